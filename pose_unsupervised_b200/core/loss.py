@@ -1,0 +1,94 @@
+"""Epipolar-consistency scoring behind the name of lib/core/loss.py:89-133.
+
+``FundamentalLoss`` keeps the reference's call signature and returns the same scalar
+(forward value; the autograd variant used while training is listed as a "next" row
+in SURVEY.md section 8f).  ``epipolar_residuals`` is the per-(frame, pair, joint) form of
+run/test/test_fund_mtx.py:56-69.  The reference reads {(subject, a, b): F} from
+data/testdata/fundamental_matrix.pkl (lib/core/loss.py:92-94); here the dict is
+passed in (or loaded from ``cfg.DATASET.ROOT`` when present).
+"""
+import itertools
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from .. import _lib, runtime as rt
+
+
+class FundamentalTable(object):
+    """{(subject, a, b): F[3,3]} packed as CUDA float64 [S, V, V, 9] + subject -> slot map."""
+
+    def __init__(self, fdict, nviews=4):
+        subjects = sorted({k[0] for k in fdict})
+        self.slot = {s: i for i, s in enumerate(subjects)}
+        self.nviews = nviews
+        host = np.zeros((len(subjects), nviews, nviews, 9))
+        for (s, a, b), F in fdict.items():
+            if a < nviews and b < nviews:
+                host[self.slot[s], a, b] = np.asarray(F, dtype=np.float64).reshape(9)
+        self.fmat = rt.to_device(host)
+
+    def slots(self, subjects):
+        subs = subjects.tolist() if hasattr(subjects, 'tolist') else list(subjects)
+        return rt.to_device(np.array([self.slot[s] for s in subs], dtype=np.int32))
+
+
+def epipolar_residuals(pred2d, subjects, fundamental, nviews=4, weight=None, return_sum=False):
+    """|x_b^T F_(subj,a,b) x_a| for the V(V-1) ordered pairs of every frame.
+
+    pred2d [B*V, J, 2] view-minor (numpy or CUDA, float32/float64); subjects [B];
+    fundamental: FundamentalTable or the reference's dict.  Returns [B, V(V-1), J] float64
+    (pairs in itertools.permutations order), optionally with the grand total.
+    """
+    rt.require_device()
+    table = fundamental if isinstance(fundamental, FundamentalTable) else FundamentalTable(fundamental, nviews)
+    xy = rt.to_device_float(pred2d)
+    N, J = int(xy.shape[0]), int(xy.shape[1])
+    B = N // nviews
+    subj = table.slots(subjects)
+    assert int(subj.shape[0]) == B, 'one subject per frame'
+    w = rt.to_device_float(weight).reshape(N, J) if weight is not None else None
+    resid = rt.empty((B, nviews * (nviews - 1), J), torch.float64)
+    total = rt.zeros((1,), torch.float64) if return_sum else None
+    _lib.call('pb200_epipolar', rt.ptr(table.fmat), rt.ptr(subj), rt.ptr(xy), rt.float_dtype_tag(xy),
+              rt.ptr(w), rt.float_dtype_tag(w) if w is not None else _lib.F64, B, nviews, J,
+              rt.ptr(resid), rt.ptr(total), rt.stream_ptr())
+    if not rt.is_device_tensor(pred2d):
+        resid = rt.to_host(resid)
+    return (resid, total) if return_sum else resid
+
+
+class FundamentalLoss(object):
+    """lib/core/loss.py:89-133 (forward scoring)."""
+
+    def __init__(self, cfg, fundamental_matrix_dict=None):
+        self.use_target_weight = cfg.LOSS.USE_TARGET_WEIGHT_FUND
+        if fundamental_matrix_dict is None:
+            path = os.path.join(cfg.DATASET.ROOT, 'testdata', 'fundamental_matrix.pkl')
+            with open(path, 'rb') as f:
+                fundamental_matrix_dict = pickle.load(f)
+        self.fundamental_matrix_dict = fundamental_matrix_dict
+        self._tables = {}
+
+    def __call__(self, joints_2d_list, target_weight, meta):
+        """joints_2d_list: V tensors [K,J,2] (image px); target_weight: V tensors [K,J,1];
+        meta: V dicts with 'subject' [K].  Returns a 0-d CUDA float64 tensor."""
+        assert isinstance(joints_2d_list[0], torch.Tensor)
+        nviews = len(joints_2d_list)
+        K, J = joints_2d_list[0].shape[:2]
+        subject = meta[0]['subject']
+        subject = subject.numpy() if isinstance(subject, torch.Tensor) else np.asarray(subject)
+        assert K == len(subject)
+        table = self._tables.get(nviews)
+        if table is None:
+            table = self._tables[nviews] = FundamentalTable(self.fundamental_matrix_dict, nviews)
+        # view-minor rows: row = sample * V + view
+        xy = torch.stack([p.detach() for p in joints_2d_list], dim=1).reshape(K * nviews, J, 2)
+        w = None
+        if self.use_target_weight:
+            w = torch.stack([t.detach() for t in target_weight], dim=1).reshape(K * nviews, J)
+        _, total = epipolar_residuals(rt.to_device(xy), subject, table, nviews, w, return_sum=True)
+        npairs = len(list(itertools.permutations(range(nviews), 2)))
+        return total[0] / (K * npairs * J)

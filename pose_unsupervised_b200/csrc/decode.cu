@@ -1,0 +1,138 @@
+// decode.cu -- K1: batched heatmap decode (get_max_preds / get_final_preds) and the
+// crop-affine pre-pass.  HBM-bound: every heatmap byte is read exactly once.
+//
+// Launch shape: 256-thread blocks (8 warps), one warp per map, warps stride over the
+// N*J maps; grid = min(ceil(maps/8), blocks_per_sm * #SM) so that the grid is a whole
+// number of resident waves on the 148 SMs.
+#include "decode.cuh"
+
+namespace pb200 {
+
+constexpr int kDecodeWarps = 8;
+
+__global__ void __launch_bounds__(kDecodeWarps * 32)
+decode_kernel(HmViews hv, int N, int J, int H, int W, int vec_ok,
+              const double* __restrict__ affine, int post_process,
+              float* __restrict__ out_xy, float* __restrict__ out_maxval,
+              int32_t* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long total = (long long)N * J;
+  const int HW = H * W;
+  for (long long m = (long long)blockIdx.x * kDecodeWarps + warp; m < total;
+       m += (long long)gridDim.x * kDecodeWarps) {
+    const int row = (int)(m / J), j = (int)(m % J);
+    const float* base = map_base(hv, row, j, J, HW);
+    const DecodeOut o = decode_map(base, H, W, vec_ok != 0,
+                                   affine ? affine + 6 * (size_t)row : nullptr,
+                                   post_process != 0, lane);
+    if (lane == 0) {
+      reinterpret_cast<float2*>(out_xy)[m] = make_float2(o.x, o.y);
+      out_maxval[m] = o.maxval;
+      if (out_idx) out_idx[m] = o.idx;
+    }
+  }
+}
+
+__global__ void crop_affine_kernel(const void* center, int c_f64, const void* scale, int s_f64, int n,
+                                   int out_w, int out_h, int inv, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double m[6];
+  crop_affine_row(center, c_f64, scale, s_f64, i, out_w, out_h, inv, m);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) out[6 * (size_t)i + k] = m[k];
+}
+
+int fill_views(const float* const* hm_views_host, int n_ptr, int N, HmViews& hv) {
+  PB_REQUIRE(hm_views_host != nullptr, "hm_views_host is null");
+  PB_REQUIRE(n_ptr >= 1 && n_ptr <= PB200_MAX_VIEWS, "n_ptr=%d outside [1,%d]", n_ptr, PB200_MAX_VIEWS);
+  PB_REQUIRE(N % n_ptr == 0, "N=%d is not a multiple of the %d view tensors", N, n_ptr);
+  hv.n = n_ptr;
+  for (int v = 0; v < PB200_MAX_VIEWS; ++v) hv.ptr[v] = v < n_ptr ? hm_views_host[v] : nullptr;
+  for (int v = 0; v < n_ptr; ++v) PB_REQUIRE(hv.ptr[v] != nullptr, "heatmap pointer %d is null", v);
+  return PB200_OK;
+}
+
+bool views_vec_ok(const HmViews& hv, int HW) {
+  if (HW % 4 != 0) return false;
+  for (int v = 0; v < hv.n; ++v)
+    if ((reinterpret_cast<uintptr_t>(hv.ptr[v]) & 15u) != 0) return false;
+  return true;
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" int pb200_crop_affine(const void* center, int center_dtype, const void* scale,
+                                 int scale_dtype, int n, int out_w, int out_h, int inv, double* out,
+                                 void* stream) {
+  PB_REQUIRE(center && scale && out, "null pointer");
+  PB_REQUIRE(n >= 0 && out_w > 0 && out_h > 0, "bad sizes n=%d out=(%d,%d)", n, out_w, out_h);
+  PB_REQUIRE((center_dtype | 1) == 1 && (scale_dtype | 1) == 1, "dtype tags must be PB200_F32/PB200_F64");
+  if (n == 0) return PB200_OK;
+  crop_affine_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      center, center_dtype, scale, scale_dtype, n, out_w, out_h, inv, out);
+  PB_LAUNCH_CHECK("crop_affine_kernel");
+  return PB200_OK;
+}
+
+extern "C" int pb200_decode(const float* const* hm_views_host, int n_ptr, int N, int J, int H, int W,
+                            const double* affine, int post_process, float* out_xy, float* out_maxval,
+                            int32_t* out_idx, void* stream) {
+  PB_REQUIRE(N >= 0 && J >= 1 && H >= 1 && W >= 1, "bad shape N=%d J=%d H=%d W=%d", N, J, H, W);
+  PB_REQUIRE((long long)H * W < (1LL << 24), "map of %dx%d exceeds the float32-exact index range", H, W);
+  PB_REQUIRE(out_xy && out_maxval, "null output");
+  HmViews hv;
+  int rc = fill_views(hm_views_host, n_ptr, N, hv);
+  if (rc != PB200_OK) return rc;
+  if (N == 0) return PB200_OK;
+  const long long maps = (long long)N * J;
+  const int sm = cached_sm_count();
+  if (sm <= 0) return PB200_ERR_CUDA;
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    int n = 0;
+    PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, decode_kernel, kDecodeWarps * 32, 0));
+    blocks_per_sm = n > 0 ? n : 1;
+  }
+  long long blocks = (maps + kDecodeWarps - 1) / kDecodeWarps;
+  const long long cap = (long long)sm * blocks_per_sm;  // one resident wave
+  if (blocks > cap) blocks = cap;
+  decode_kernel<<<(unsigned)blocks, kDecodeWarps * 32, 0, (cudaStream_t)stream>>>(
+      hv, N, J, H, W, views_vec_ok(hv, H * W) ? 1 : 0, affine, post_process, out_xy, out_maxval,
+      out_idx);
+  PB_LAUNCH_CHECK("decode_kernel");
+  return PB200_OK;
+}
+
+// ---- transform_preds on already decoded coordinates ----------------------------------
+namespace pb200 {
+template <typename T>
+__global__ void transform_preds_kernel(const T* __restrict__ coords, const double* __restrict__ affine,
+                                       long long n, int J, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* t = affine + 6 * (i / J);
+  const double x = (double)coords[2 * i], y = (double)coords[2 * i + 1];
+  out[2 * i] = fma(y, t[1], x * t[0]) + t[2];
+  out[2 * i + 1] = fma(y, t[4], x * t[3]) + t[5];
+}
+}  // namespace pb200
+
+extern "C" int pb200_transform_preds(const void* coords, int coords_dtype, const double* affine, int N,
+                                     int J, double* out, void* stream) {
+  PB_REQUIRE(coords && affine && out, "null pointer");
+  PB_REQUIRE(N >= 0 && J >= 1, "bad shape");
+  PB_REQUIRE((coords_dtype | 1) == 1, "coords_dtype must be PB200_F32/PB200_F64");
+  const long long n = (long long)N * J;
+  if (n == 0) return PB200_OK;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (coords_dtype == PB200_F32)
+    pb200::transform_preds_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)coords, affine, n, J, out);
+  else
+    pb200::transform_preds_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((const double*)coords, affine, n, J, out);
+  PB_LAUNCH_CHECK("transform_preds_kernel");
+  return PB200_OK;
+}

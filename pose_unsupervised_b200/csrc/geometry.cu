@@ -1,0 +1,300 @@
+// geometry.cu -- K0 (projection), K2/K3 (triangulate / reproject / RANSAC from 2D
+// locations), epipolar residual and MPJPE partial sums.
+//
+// These kernels work on a few hundred bytes per frame (the pseudo-label pass of
+// run/test/test_pseudo_label.py starts from 2D locations, not heatmaps), so they are
+// latency / FP64-issue bound, not HBM bound: one thread per (frame, joint), float64
+// throughout, 128-thread blocks so that every SM holds many independent joints.
+#include "lift.cuh"
+
+namespace pb200 {
+
+template <typename T>
+struct XYLoader {
+  const T* base;  // &xy[frame*V, j, 0]
+  int row_stride; // J*2
+  __device__ __forceinline__ void operator()(int v, double& x, double& y) const {
+    const T* p = base + (size_t)v * row_stride;
+    x = (double)p[0];
+    y = (double)p[1];
+  }
+};
+
+enum { kModeTriangulate = 0, kModeReproject = 1, kModeRansac = 2 };
+
+struct GeoParams {
+  const double* campack;
+  const int32_t* cam_index;
+  const void* xy;
+  const uint8_t* vis;
+  int B, V, J;
+  int no_dist;
+  double reproj_thre;
+  int num_inliers;
+  double* out_X;
+  double* out_proj;
+  uint8_t* out_vis;
+  double* out_err;
+};
+
+template <typename T, int kMode>
+__global__ void __launch_bounds__(128) geometry_kernel(GeoParams p) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)p.B * p.J) return;
+  const int f = (int)(t / p.J), j = (int)(t % p.J);
+  const int V = p.V, J = p.J;
+  const size_t row0 = (size_t)f * V;
+  const int32_t* cam_row = p.cam_index + row0;
+  XYLoader<T> xy{reinterpret_cast<const T*>(p.xy) + (row0 * J + j) * 2, J * 2};
+  uint32_t mask = 0u;
+  for (int v = 0; v < V; ++v)
+    if (p.vis == nullptr || p.vis[(row0 + v) * J + j]) mask |= 1u << v;
+  const bool nd = p.no_dist != 0;
+
+  if (kMode == kModeRansac) {
+    const uint32_t in = ransac_joint(p.campack, cam_row, V, nd, mask, xy, p.reproj_thre, p.num_inliers);
+    for (int v = 0; v < V; ++v) p.out_vis[(row0 + v) * J + j] = (in >> v) & 1u;
+    return;
+  }
+
+  double X[3];
+  const int nv = triangulate_joint(p.campack, cam_row, V, nd, mask, xy, X);
+  if (p.out_X) {
+    double* o = p.out_X + ((size_t)f * J + j) * 3;
+    o[0] = X[0]; o[1] = X[1]; o[2] = X[2];
+  }
+  if (kMode == kModeReproject) {
+    for (int v = 0; v < V; ++v) {
+      double pu = 0.0, pv = 0.0, e = 0.0;
+      if (nv >= 2) e = reproject_view(p.campack, cam_row, v, nd, X, xy, pu, pv);
+      const size_t o = (row0 + v) * J + j;
+      p.out_proj[2 * o] = pu;
+      p.out_proj[2 * o + 1] = pv;
+      p.out_vis[o] = nv >= 2 ? 1 : 0;
+      if (p.out_err) p.out_err[o] = e;
+    }
+  }
+}
+
+__global__ void project_kernel(const double* __restrict__ campack, int cam_id,
+                               const double* __restrict__ pts, int n, int model,
+                               double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Cam c;
+  load_cam(campack + (size_t)cam_id * PB200_CAM_STRIDE, c);
+  const double X[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+  double u, v;
+  if (model == 0) project_h36m(c, X, u, v);
+  else project_plumb_bob(c, X, model == 1, u, v);
+  out[2 * i] = u;
+  out[2 * i + 1] = v;
+}
+
+// Block-wide sum of one double per thread (fixed tree order), result in thread 0.
+template <int kThreads>
+__device__ __forceinline__ double block_sum(double v, double* smem) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < kThreads / 32; ++w) s += smem[w];
+  __syncthreads();
+  return s;
+}
+
+// thread per (frame, pair, joint); pairs in itertools.permutations(range(V), 2) order
+template <typename T, typename TW>
+__global__ void __launch_bounds__(256)
+epipolar_kernel(const double* __restrict__ fmat, const int32_t* __restrict__ subj,
+                const T* __restrict__ xy, const TW* __restrict__ w, int B, int V, int J,
+                double* __restrict__ out_resid, double* __restrict__ out_sum) {
+  __shared__ double red[8];
+  const int P = V * (V - 1);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double r = 0.0;
+  if (t < (long long)B * P * J) {
+    const int j = (int)(t % J);
+    const int pr = (int)((t / J) % P);
+    const int f = (int)(t / ((long long)J * P));
+    const int a = pr / (V - 1);
+    int b = pr % (V - 1);
+    if (b >= a) ++b;
+    const double* F = fmat + (((size_t)subj[f] * V + a) * V + b) * 9;
+    const size_t ra = ((size_t)f * V + a) * J + j, rb = ((size_t)f * V + b) * J + j;
+    const double xa = (double)xy[2 * ra], ya = (double)xy[2 * ra + 1];
+    const double xb = (double)xy[2 * rb], yb = (double)xy[2 * rb + 1];
+    // [x_b, y_b, 1] @ F  (BLAS accumulation order), then sum(. * [x_a, y_a, 1])
+    const double t0 = fma(yb, F[3], xb * F[0]) + F[6];
+    const double t1 = fma(yb, F[4], xb * F[1]) + F[7];
+    const double t2 = fma(yb, F[5], xb * F[2]) + F[8];
+    r = fabs((t0 * xa + t1 * ya) + t2);
+    if (w != nullptr) r = r * ((double)w[rb] * (double)w[ra]);
+    out_resid[t] = r;
+  }
+  if (out_sum != nullptr) {
+    const double s = block_sum<256>(r, red);
+    if (threadIdx.x == 0) atomicAdd(out_sum, s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mpjpe_kernel(const double* __restrict__ pred, const double* __restrict__ gt, long long n,
+             double* __restrict__ out4) {
+  __shared__ double red[8];
+  double s = 0.0, s2 = 0.0, mx = 0.0, cnt = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double dx = pred[3 * i] - gt[3 * i], dy = pred[3 * i + 1] - gt[3 * i + 1],
+                 dz = pred[3 * i + 2] - gt[3 * i + 2];
+    const double d = sqrt(dx * dx + dy * dy + dz * dz);
+    s += d; s2 += d * d; mx = fmax(mx, d); cnt += 1.0;
+  }
+  const double bs = block_sum<256>(s, red);
+  const double bs2 = block_sum<256>(s2, red);
+  const double bc = block_sum<256>(cnt, red);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off));
+  if ((threadIdx.x & 31) == 0)  // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(out4 + 2), (unsigned long long)__double_as_longlong(mx));
+  if (threadIdx.x == 0) {
+    atomicAdd(out4, bs);
+    atomicAdd(out4 + 1, bs2);
+    atomicAdd(out4 + 3, bc);
+  }
+}
+
+static int check_geo(const double* campack, const int32_t* cam_index, const void* xy, int xy_dtype,
+                     int B, int V, int J) {
+  PB_REQUIRE(campack && cam_index && xy, "null input pointer");
+  PB_REQUIRE(B >= 0 && J >= 1, "bad shape B=%d J=%d", B, J);
+  PB_REQUIRE(V >= 2 && V <= PB200_MAX_VIEWS, "V=%d outside [2,%d]", V, PB200_MAX_VIEWS);
+  PB_REQUIRE((xy_dtype | 1) == 1, "xy_dtype must be PB200_F32/PB200_F64");
+  return PB200_OK;
+}
+
+template <int kMode>
+static int launch_geo(const GeoParams& p, int xy_dtype, void* stream) {
+  const long long n = (long long)p.B * p.J;
+  if (n == 0) return PB200_OK;
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  if (xy_dtype == PB200_F32)
+    geometry_kernel<float, kMode><<<blocks, 128, 0, (cudaStream_t)stream>>>(p);
+  else
+    geometry_kernel<double, kMode><<<blocks, 128, 0, (cudaStream_t)stream>>>(p);
+  PB_LAUNCH_CHECK("geometry_kernel");
+  return PB200_OK;
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" int pb200_project(const double* campack, int cam_id, const double* pts, int n, int model,
+                             double* out, void* stream) {
+  PB_REQUIRE(campack && pts && out, "null pointer");
+  PB_REQUIRE(n >= 0 && cam_id >= 0, "bad n=%d cam_id=%d", n, cam_id);
+  PB_REQUIRE(model >= 0 && model <= 2, "model must be 0 (h36m), 1 (plumb-bob) or 2 (pin-hole)");
+  if (n == 0) return PB200_OK;
+  project_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(campack, cam_id, pts, n, model, out);
+  PB_LAUNCH_CHECK("project_kernel");
+  return PB200_OK;
+}
+
+extern "C" int pb200_triangulate(const double* campack, const int32_t* cam_index, const void* xy,
+                                 int xy_dtype, const uint8_t* vis, int B, int V, int J,
+                                 int no_distortion, double* out_X, void* stream) {
+  int rc = check_geo(campack, cam_index, xy, xy_dtype, B, V, J);
+  if (rc != PB200_OK) return rc;
+  PB_REQUIRE(out_X, "out_X is null");
+  GeoParams p{campack, cam_index, xy, vis, B, V, J, no_distortion, 0.0, 0, out_X, nullptr, nullptr, nullptr};
+  return launch_geo<kModeTriangulate>(p, xy_dtype, stream);
+}
+
+extern "C" int pb200_reproject(const double* campack, const int32_t* cam_index, const void* xy,
+                               int xy_dtype, const uint8_t* vis, int B, int V, int J,
+                               int no_distortion, double* out_proj, uint8_t* out_vis, double* out_X,
+                               double* out_err, void* stream) {
+  int rc = check_geo(campack, cam_index, xy, xy_dtype, B, V, J);
+  if (rc != PB200_OK) return rc;
+  PB_REQUIRE(out_proj && out_vis, "out_proj / out_vis is null");
+  GeoParams p{campack, cam_index, xy, vis, B, V, J, no_distortion, 0.0, 0, out_X, out_proj, out_vis, out_err};
+  return launch_geo<kModeReproject>(p, xy_dtype, stream);
+}
+
+extern "C" int pb200_ransac(const double* campack, const int32_t* cam_index, const void* xy,
+                            int xy_dtype, const uint8_t* vis, int B, int V, int J, int no_distortion,
+                            double reproj_thre, int num_inliers, uint8_t* out_vis, void* stream) {
+  int rc = check_geo(campack, cam_index, xy, xy_dtype, B, V, J);
+  if (rc != PB200_OK) return rc;
+  PB_REQUIRE(out_vis, "out_vis is null");
+  PB_REQUIRE(num_inliers >= 1, "num_inliers must be >= 1 (the reference divides by it)");
+  GeoParams p{campack, cam_index, xy, vis, B, V, J, no_distortion, reproj_thre, num_inliers,
+              nullptr, nullptr, out_vis, nullptr};
+  return launch_geo<kModeRansac>(p, xy_dtype, stream);
+}
+
+extern "C" int pb200_epipolar(const double* fmat, const int32_t* subj_index, const void* xy,
+                              int xy_dtype, const void* weight, int w_dtype, int B, int V, int J,
+                              double* out_resid, double* out_sum, void* stream) {
+  PB_REQUIRE(fmat && subj_index && xy && out_resid, "null pointer");
+  PB_REQUIRE(B >= 0 && J >= 1 && V >= 2 && V <= PB200_MAX_VIEWS, "bad shape B=%d V=%d J=%d", B, V, J);
+  PB_REQUIRE((xy_dtype | 1) == 1 && (w_dtype | 1) == 1, "dtype tags must be PB200_F32/PB200_F64");
+  const long long n = (long long)B * V * (V - 1) * J;
+  if (n == 0) return PB200_OK;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  cudaStream_t s = (cudaStream_t)stream;
+#define PB_EPI(T, TW) \
+  epipolar_kernel<T, TW><<<blocks, 256, 0, s>>>(fmat, subj_index, (const T*)xy, (const TW*)weight, B, V, J, out_resid, out_sum)
+  if (xy_dtype == PB200_F32) { if (w_dtype == PB200_F32) PB_EPI(float, float); else PB_EPI(float, double); }
+  else { if (w_dtype == PB200_F32) PB_EPI(double, float); else PB_EPI(double, double); }
+#undef PB_EPI
+  PB_LAUNCH_CHECK("epipolar_kernel");
+  return PB200_OK;
+}
+
+extern "C" int pb200_mpjpe_stats(const double* pred, const double* gt, int B, int J, double* out4,
+                                 void* stream) {
+  PB_REQUIRE(pred && gt && out4, "null pointer");
+  PB_REQUIRE(B >= 0 && J >= 1, "bad shape");
+  const long long n = (long long)B * J;
+  if (n == 0) return PB200_OK;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)cached_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  mpjpe_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, n, out4);
+  PB_LAUNCH_CHECK("mpjpe_kernel");
+  return PB200_OK;
+}
+
+// ---- world <-> camera frame (lib/multiviews/cameras.py:57-82) -------------------------
+namespace pb200 {
+__global__ void frame_change_kernel(const double* __restrict__ R, const double* __restrict__ T,
+                                    const double* __restrict__ pts, int n, int to_world,
+                                    double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+  if (!to_world) {  // R (x - T)
+    const double dx = x - T[0], dy = y - T[1], dz = z - T[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) out[3 * i + r] = fma(R[3 * r + 2], dz, fma(R[3 * r + 1], dy, R[3 * r] * dx));
+  } else {          // R^T x + T
+#pragma unroll
+    for (int r = 0; r < 3; ++r) out[3 * i + r] = fma(R[6 + r], z, fma(R[3 + r], y, R[r] * x)) + T[r];
+  }
+}
+}  // namespace pb200
+
+extern "C" int pb200_frame_change(const double* R, const double* T, const double* pts, int n,
+                                  int to_world, double* out, void* stream) {
+  PB_REQUIRE(R && T && pts && out, "null pointer");
+  PB_REQUIRE(n >= 0, "bad n");
+  if (n == 0) return PB200_OK;
+  pb200::frame_change_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(R, T, pts, n, to_world, out);
+  PB_LAUNCH_CHECK("frame_change_kernel");
+  return PB200_OK;
+}

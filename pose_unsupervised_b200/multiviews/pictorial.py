@@ -1,0 +1,155 @@
+"""Recursive pictorial structure model behind the names of lib/multiviews/pictorial.py.
+
+``rpsm`` keeps the reference's signature (lib/multiviews/pictorial.py:214-250) for one
+frame; ``rpsm_batch`` runs a batch of frames, one thread block per frame
+(csrc/rpsm.cu).  The level-0 ``pairwise_constraint`` dict of scipy sparse matrices
+({(parent, child): [nbins, nbins]}, run/test/test_rpsm.py:131-135) is converted once
+into a device bit matrix (``PairwiseTable``) and cached; ``PairwiseTable.from_limb_lengths``
+builds it on the GPU from average limb lengths instead of the reference's offline
+O(n^6) Python generator (run/test/generate_pairwise_constraints.py:60-95).
+"""
+import numpy as np
+import torch
+
+from .. import _lib, runtime as rt
+from ..utils.transforms import crop_affine
+from .body import HumanBody
+from .cameras import CameraTable
+
+
+class PairwiseTable(object):
+    """Level-0 pairwise constraints as bits: [E, nbins, ceil(nbins/32)] uint32 on the device."""
+
+    _cache = {}
+
+    def __init__(self, bits, nbins):
+        self.bits = bits
+        self.nbins = nbins
+
+    @classmethod
+    def from_dict(cls, pairwise, body):
+        """{(parent, child): sparse or dense [nbins, nbins]} -> table (cached per dict object)."""
+        if isinstance(pairwise, PairwiseTable):
+            return pairwise
+        key = (id(pairwise), torch.cuda.current_device())
+        hit = cls._cache.get(key)
+        if hit is not None and hit[0] is pairwise:
+            return hit[1]
+        rows = []
+        for e in body.edges():
+            m = pairwise[e]
+            m = m.toarray() if hasattr(m, 'toarray') else np.asarray(m)
+            nb = m.shape[0]
+            if m.shape != (nb, nb):
+                raise ValueError('pairwise[%s] must be square' % (e,))
+            if not np.all((m == 0) | (m == 1)):
+                raise ValueError('pairwise[%s] must hold only 0/1 (generate_pairwise_constraints.py:93)' % (e,))
+            words = (nb + 31) // 32
+            padded = np.zeros((nb, words * 32), dtype=np.uint8)
+            padded[:, :nb] = m != 0
+            rows.append(np.packbits(padded, axis=1, bitorder='little').view('<u4'))
+        host = np.stack(rows).astype(np.uint32)
+        table = cls(rt.to_device(host.view(np.int32)), host.shape[1])
+        if len(cls._cache) > 4:
+            cls._cache.clear()
+        cls._cache[key] = (pairwise, table)
+        return table
+
+    @classmethod
+    def from_limb_lengths(cls, avg_limb_length, body, box_size=2000, nbins=16):
+        """P[i,j] = | |g_i - g_j| - L | < 0.4 L on the zero-centred grid, built on the GPU."""
+        rt.require_device()
+        edges = body.edges()
+        limb = rt.to_device(np.array([avg_limb_length[e] for e in edges], dtype=np.float64))
+        nb = nbins ** 3
+        bits = rt.empty((len(edges), nb, (nb + 31) // 32), torch.int32)
+        _lib.call('pb200_pairwise_level0', rt.ptr(limb), len(edges), int(nbins), float(box_size),
+                  rt.ptr(bits), rt.stream_ptr())
+        return cls(bits, nb)
+
+    def to_dense(self, edge_index):
+        """Host bool [nbins, nbins] of one edge (tests, inspection)."""
+        w = self.bits[edge_index].cpu().numpy().view(np.uint32)
+        bits = np.unpackbits(w.view(np.uint8), axis=1, bitorder='little')
+        return bits[:, :self.nbins].astype(bool)
+
+
+def rpsm_batch(cams, heatmaps, boxes_center, boxes_scale, grid_centers, limb_lengths, pairwise,
+               config, body=None, return_trace=False):
+    """RPSM for B frames.
+
+    cams         : CameraTable or list of B*V camera dicts (view-minor rows)
+    heatmaps     : [B, V, J, H, W] float32 (numpy or CUDA)
+    boxes_center : [B*V, 2], boxes_scale [B*V, 2] crop boxes the heatmaps were computed on
+    grid_centers : [B, 3] float64 root locations
+    limb_lengths : [B, E] float64 in ``body.edges()`` order
+    pairwise     : PairwiseTable or the reference's dict
+    Returns poses [B, J, 3] float64 (CUDA tensor if heatmaps is one), optionally the chosen
+    bins per level [B, depth+1, J] int32.
+    """
+    rt.require_device()
+    body = HumanBody() if body is None else body
+    hm = rt.to_device(heatmaps)
+    if hm.dtype != torch.float32 or hm.dim() != 5:
+        raise TypeError('heatmaps must be float32 [B, V, J, H, W]')
+    B, V, J, H, W = [int(v) for v in hm.shape]
+    if J != len(body.skeleton):
+        raise ValueError('heatmaps have %d joints, the body %d' % (J, len(body.skeleton)))
+    if H != W:
+        # the reference builds its interpolator on (arange(h), arange(w)) with hmap.T,
+        # which only works for square maps (lib/multiviews/pictorial.py:176-186)
+        raise ValueError('RPSM needs square heatmaps')
+    table = CameraTable.from_cameras(cams)
+    ps = config.PICT_STRUCT
+    img = config.NETWORK.IMAGE_SIZE
+    aff = crop_affine(boxes_center, boxes_scale, (int(img[0]), int(img[1])), inv=0)
+    if aff.shape[0] != B * V or len(table) < B * V:
+        raise ValueError('need one camera and one box per (frame, view) row')
+    edges, order, root_idx = body.tree_arrays()
+    E = len(edges)
+    root = rt.to_device(np.asarray(grid_centers, dtype=np.float64).reshape(B, 3)
+                        if not isinstance(grid_centers, torch.Tensor) else grid_centers, torch.float64)
+    limb = rt.to_device(np.asarray(limb_lengths, dtype=np.float64).reshape(B, E)
+                        if not isinstance(limb_lengths, torch.Tensor) else limb_lengths, torch.float64)
+    pw = PairwiseTable.from_dict(pairwise, body)
+    n0 = int(ps.FIRST_NBINS)
+    if pw.nbins != n0 ** 3 or pw.bits.shape[0] != E:
+        raise ValueError('pairwise table is %s, expected [%d, %d, .]' % (tuple(pw.bits.shape), E, n0 ** 3))
+    lib = _lib.load()
+    nbytes = lib.pb200_rpsm_workspace_bytes(B, J, n0, lib.pb200_sm_count())
+    ws = rt.workspace('rpsm', nbytes)
+    d_edges, d_order = rt.to_device(edges), rt.to_device(order)
+    depth = int(ps.RECUR_DEPTH)
+    pose = rt.empty((B, J, 3), torch.float64)
+    trace = rt.empty((B, depth + 1, J), torch.int32) if return_trace else None
+    _lib.call('pb200_rpsm', rt.ptr(hm), B, V, J, H, W, rt.ptr(table.pack), rt.ptr(table.index),
+              rt.ptr(aff), int(img[0]), int(img[1]), rt.ptr(root), rt.ptr(limb),
+              rt.ptr(d_edges), rt.ptr(d_order), root_idx, rt.ptr(pw.bits),
+              n0, int(ps.RECUR_NBINS), depth, float(ps.GRID_SIZE), float(ps.LIMB_LENGTH_TOLERANCE),
+              rt.ptr(ws), int(ws.numel()), rt.ptr(pose), rt.ptr(trace), rt.stream_ptr())
+    if not rt.is_device_tensor(heatmaps):
+        pose = rt.to_host(pose)
+        trace = rt.to_host(trace) if return_trace else None
+    return (pose, trace) if return_trace else pose
+
+
+def rpsm(cams, heatmaps, boxes, grid_center, limb_length, pairwise_constraint, config, body=None):
+    """lib/multiviews/pictorial.py:214-250 for one frame -> pose3d [J,3] float64.
+
+    cams: V camera dicts; heatmaps [V,J,H,W]; boxes: V dicts {center, scale};
+    limb_length {(parent, child): mm}; pairwise_constraint: the reference's dict (or a
+    PairwiseTable).
+    """
+    body = HumanBody() if body is None else body
+    hm = np.asarray(heatmaps)
+    # keep float32 boxes float32: `scale * 200.0` is rounded in the dtype of `scale`
+    # (lib/utils/transforms.py:84)
+    def stack(key):
+        vals = [np.asarray(b[key]).reshape(-1)[:2] for b in boxes]
+        f32 = all(v.dtype == np.float32 for v in vals)
+        return np.array(vals, dtype=np.float32 if f32 else np.float64)
+    centers, scales = stack('center'), stack('scale')
+    limb = np.array([limb_length[e] for e in body.edges()], dtype=np.float64)[None]
+    return rpsm_batch(list(cams), hm[None], centers, scales,
+                      np.asarray(grid_center, dtype=np.float64).reshape(1, 3), limb,
+                      pairwise_constraint, config, body)[0]

@@ -1,0 +1,69 @@
+"""Frame-sharded multi-GPU driver: one process per GPU, NCCL over NVLink.
+
+Frames are independent in every stage of the lifting path, so the
+data path has no collective: rank r owns the contiguous frame block
+[r*B/R, (r+1)*B/R) of the view-minor arrays.  The only exchange step comes after
+the compute: an all-gather of the per-frame 3D poses and an all-reduce of the MPJPE
+partial sums (run/test/test_triangulate.py:98-101), both issued on the compute
+stream.  The same code runs on CPU tensors with the gloo backend (tests).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def frame_shard(nframes, rank, world):
+    """Contiguous frame range of ``rank``; the remainder goes to the last rank."""
+    per = nframes // world
+    lo = rank * per
+    hi = nframes if rank == world - 1 else lo + per
+    return lo, hi
+
+
+def shard_rows(array, nviews, rank, world):
+    """Rows [B*V, ...] view-minor -> the rows of this rank's frames."""
+    nframes = array.shape[0] // nviews
+    lo, hi = frame_shard(nframes, rank, world)
+    return array[lo * nviews:hi * nviews]
+
+
+def gather_poses(local_poses, nframes, group=None):
+    """All-gather of per-frame 3D poses: local [B_r, J, 3] -> [nframes, J, 3] on every rank."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local_poses
+    sizes = [frame_shard(nframes, r, world) for r in range(world)]
+    counts = [hi - lo for lo, hi in sizes]
+    tail = tuple(local_poses.shape[1:])
+    if len(set(counts)) == 1:
+        out = local_poses.new_empty((nframes,) + tail)
+        dist.all_gather_into_tensor(out, local_poses.contiguous(), group=group)
+        return out
+    # uneven split (the last rank takes the remainder): pad to the largest shard so that one
+    # fixed-size all-gather suffices, then drop the padding
+    cap = max(counts)
+    padded = local_poses.new_zeros((cap,) + tail)
+    padded[:local_poses.shape[0]] = local_poses
+    gathered = local_poses.new_empty((world * cap,) + tail)
+    dist.all_gather_into_tensor(gathered, padded, group=group)
+    gathered = gathered.reshape((world, cap) + tail)
+    return torch.cat([gathered[r, :counts[r]] for r in range(world)], dim=0)
+
+
+def reduce_mpjpe(stats, group=None):
+    """All-reduce of [sum, sumsq, max, count]: SUM for 0,1,3 and MAX for 2."""
+    if dist.get_world_size(group) == 1:
+        return stats
+    sums = stats[[0, 1, 3]].clone()
+    mx = stats[2:3].clone()
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    return torch.stack([sums[0], sums[1], mx[0], sums[2]])
+
+
+def max_over_ranks(value, device, group=None):
+    """Scalar max over ranks (timing: a step takes as long as its slowest rank)."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

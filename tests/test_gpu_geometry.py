@@ -1,0 +1,162 @@
+"""GPU parity: projection, triangulation, reprojection, RANSAC, epipolar residual and MPJPE
+partial sums against the oracle (tolerance from BASELINE.json: 3D joints within 1e-2 mm)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cameras as ocam
+from oracle import epipolar as oepi
+from oracle import triangulate as otri
+from pose_unsupervised_b200.utils import synth
+from tests.util import golden, pseudo_config, unpack_cam
+
+pytestmark = pytest.mark.gpu
+
+TOL_MM = 1e-2      # north_star: within 1e-2 mm of the float64 SVD triangulation
+TOL_PX = 1e-6
+
+
+@pytest.fixture(scope='module')
+def tri():
+    from pose_unsupervised_b200.multiviews import triangulate
+    return triangulate
+
+
+def _scene(nviews, nframes, noise, distorted=True, outliers=0.0, seed=0):
+    rigs = synth.camera_table(3, nviews, seed=seed)
+    poses = synth.random_poses(nframes, seed=seed + 1)
+    rng = np.random.default_rng(seed + 2)
+    obs, cams = synth.multiview_observations(poses, rigs, rng.integers(0, 3, nframes), noise_px=noise,
+                                             outlier_frac=outliers, seed=seed + 3, distorted=distorted)
+    return poses, obs, cams
+
+
+def test_project_pose_vs_reference_golden():
+    from pose_unsupervised_b200.multiviews import cameras
+    c = golden('cameras.npz')
+    for i, v in enumerate(c['cams']):
+        cam = unpack_cam(v)
+        assert np.abs(cameras.project_pose(c['pts'], cam) - c['proj'][i]).max() < 1e-9
+        assert np.abs(cameras.world_to_camera_frame(c['pts'], cam['R'], cam['T']) - c['w2c'][i]).max() < 1e-9
+        assert np.abs(cameras.camera_to_world_frame(c['w2c'][i], cam['R'], cam['T']) - c['c2w'][i]).max() < 1e-9
+        rig = otri.build_multi_camera_system([('c', cam)])
+        ref = np.array([rig.find2d('c', p) for p in c['pts'][:16]])
+        assert np.abs(cameras.project_pose_plumb_bob(c['pts'][:16], cam) - ref).max() < 1e-8
+
+
+@pytest.mark.parametrize('nviews', [2, 4, 8])
+@pytest.mark.parametrize('no_distortion', [False, True])
+def test_triangulate_vs_oracle(tri, nviews, no_distortion):
+    poses, obs, cams = _scene(nviews, 40, 2.0, distorted=not no_distortion)
+    ref = otri.triangulate_poses(cams, obs, None, no_distortion, nviews=nviews)
+    out = tri.triangulate_poses(cams, obs, None, no_distortion, nviews=nviews)
+    assert out.dtype == np.float64 and out.shape == ref.shape
+    assert np.abs(out - ref).max() < TOL_MM
+    out32 = tri.triangulate_poses(cams, obs.astype(np.float32), None, no_distortion, nviews=nviews)
+    ref32 = otri.triangulate_poses(cams, obs.astype(np.float32), None, no_distortion, nviews=nviews)
+    assert np.abs(out32 - ref32).max() < TOL_MM
+
+
+def test_noise_free_round_trip_full_batch(tri):
+    poses, obs, cams = _scene(4, 2048, 0.0, distorted=False)
+    out = tri.triangulate_poses(cams, obs, None, True)
+    assert np.abs(out - poses).max() < 1e-5
+
+
+def test_visibility_rules(tri):
+    poses, obs, cams = _scene(4, 30, 1.0)
+    rng = np.random.default_rng(3)
+    vis = (rng.random(obs.shape[:2]) > 0.35).astype(np.float64)
+    vis[0:3, 5] = 0
+    vis[4:8, 2] = 0
+    ref = otri.triangulate_poses(cams, obs, vis)
+    out = tri.triangulate_poses(cams, obs, vis)
+    assert np.abs(out - ref).max() < TOL_MM
+    assert np.all(out[0, 5] == 0) and np.all(out[1, 2] == 0)
+    rproj, rvis, rpts = otri.reproject_poses(obs, cams, vis, return_points=True)
+    proj, pvis, pts = tri.reproject_poses(obs, cams, vis, return_points=True)
+    assert proj.dtype == obs.dtype and pvis.dtype == vis.dtype
+    assert np.array_equal(pvis, rvis)
+    assert np.abs(proj - rproj).max() < TOL_PX * 100 and np.abs(pts - rpts).max() < TOL_MM
+    bvis = vis.astype(bool)
+    proj_b, pvis_b = tri.reproject_poses(obs.astype(np.float32), cams, bvis)
+    assert proj_b.dtype == np.float32 and pvis_b.dtype == bool and np.array_equal(pvis_b, rvis.astype(bool))
+
+
+@pytest.mark.parametrize('nviews,num_inliers', [(4, 3), (4, 4), (4, 2), (8, 5)])
+def test_ransac_vs_oracle(tri, nviews, num_inliers):
+    poses, obs, cams = _scene(nviews, 48, 2.0, outliers=0.15, seed=7)
+    rng = np.random.default_rng(9)
+    vis = (rng.random(obs.shape[:2]) > 0.1).astype(np.float64)
+    for nd in (False, True):
+        ref = otri.ransac(obs, cams, vis, 10.0, num_inliers, nd, nviews=nviews)
+        out = tri.ransac(obs, cams, vis, pseudo_config(10.0, num_inliers, nd), nviews=nviews)
+        assert out.dtype == vis.dtype
+        # selection is discrete: a reprojection error within 1e-6 px of the threshold may flip
+        assert (out != ref).mean() < 1e-3
+        assert 0.2 < ref.mean() < 1.0
+
+
+def test_epipolar_vs_oracle():
+    from pose_unsupervised_b200.core.loss import FundamentalLoss, epipolar_residuals
+    rigs = synth.camera_table(3, 4, seed=11)
+    poses = synth.random_poses(33, seed=12)
+    subj = np.random.default_rng(13).integers(0, 3, 33)
+    obs, _ = synth.multiview_observations(poses, rigs, subj, noise_px=2.0, seed=14, distorted=False)
+    F = oepi.fundamental_table({s: rigs[s] for s in range(3)})
+    ref = oepi.epipolar_residuals(obs, subj, F)
+    out = epipolar_residuals(obs, subj, F)
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    # FundamentalLoss call signature (lib/core/loss.py:101-133), float32 like the training loop
+    import types
+    views = [torch.from_numpy(obs.reshape(33, 4, 17, 2)[:, v]).float().cuda() for v in range(4)]
+    w = [torch.from_numpy(np.random.default_rng(v).random((33, 17, 1))).float().cuda() for v in range(4)]
+    meta = [{'subject': torch.from_numpy(subj)} for _ in range(4)]
+    for use_w in (False, True):
+        cfg = types.SimpleNamespace(LOSS=types.SimpleNamespace(USE_TARGET_WEIGHT_FUND=use_w))
+        loss = FundamentalLoss(cfg, F)(views, w, meta)
+        ref_loss = oepi.fundamental_loss([v.cpu().numpy().astype(np.float64) for v in views],
+                                         [x.cpu().numpy().astype(np.float64) for x in w], subj, F, use_w)
+        assert abs(float(loss) - ref_loss) < 1e-9 * max(1.0, abs(ref_loss))
+
+
+def test_mpjpe_stats(tri):
+    rng = np.random.default_rng(0)
+    pred, gt = rng.normal(0, 100, (3000, 17, 3)), rng.normal(0, 100, (3000, 17, 3))
+    norm = np.linalg.norm(pred - gt, axis=2)
+    s = tri.mpjpe_summary(tri.mpjpe_stats(pred, gt))
+    assert abs(s['mean'] - norm.mean()) < 1e-9 and abs(s['std'] - norm.std()) < 1e-6
+    assert s['max'] == norm.max() and s['count'] == norm.size
+
+
+def test_pseudo_label_pipeline_full_size(tri):
+    """Config 4(ii) shape on one GPU slice: 100k frames from 2D locations; properties that do
+    not need the oracle at this size, plus the oracle on a slice."""
+    B = 100000
+    rigs = synth.camera_table(7, 4, seed=21)
+    rng = np.random.default_rng(22)
+    base = synth.random_poses(512, seed=23)
+    poses = base[rng.integers(0, 512, B)] + rng.normal(0, 20, (B, 17, 3))
+    subj = rng.integers(0, 7, B)
+    from pose_unsupervised_b200.multiviews.cameras import CameraTable, pack_camera
+    pack = np.array([pack_camera(c) for rig in rigs for c in rig])
+    index = (subj[:, None] * 4 + np.arange(4)[None]).reshape(-1).astype(np.int32)
+    table = CameraTable.from_arrays(pack, index)
+    obs = np.empty((B * 4, 17, 2))
+    for s in range(7):
+        sel = np.where(subj == s)[0]
+        for v in range(4):
+            pts = poses[sel].reshape(-1, 3)
+            obs[sel * 4 + v] = synth.project_plumb_bob_numpy(pts, rigs[s][v]).reshape(len(sel), 17, 2)
+    clean = tri.triangulate_poses(table, obs)
+    assert np.abs(clean - poses).max() < 2.0                        # 5-iteration undistortion residual
+    noisy = obs + rng.normal(0, 2.0, obs.shape)
+    vis = np.ones(noisy.shape[:2])
+    proj, pvis, pts = tri.reproject_poses(noisy, table, vis, return_points=True)
+    assert pvis.all() and np.linalg.norm(pts - poses, axis=2).mean() < 15.0
+    assert np.linalg.norm(proj - noisy, axis=2).mean() < 4.0
+    sl = slice(1000, 1016)
+    cams = [rigs[subj[i]][v] for i in range(sl.start, sl.stop) for v in range(4)]
+    ref = otri.triangulate_poses(cams, noisy[sl.start * 4:sl.stop * 4])
+    assert np.abs(pts[sl] - ref).max() < TOL_MM

@@ -1,0 +1,133 @@
+"""CPU tests of the kernels' float64 arithmetic.
+
+csrc/lift_math.cuh is plain C++ marked __host__ __device__; tests/hostcheck builds it
+with g++ (TEST-ONLY, never loaded by the package) so that the exact device arithmetic
+can be compared with the oracle and the reference goldens without a GPU.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import triangulate as otri
+from pose_unsupervised_b200.multiviews.cameras import pack_camera
+from pose_unsupervised_b200.utils import synth
+from tests.util import golden
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, 'hostcheck', 'hostcheck.cpp')
+SO = os.path.join(HERE, 'hostcheck', '_hostcheck.so')
+
+
+@pytest.fixture(scope='module')
+def hc():
+    if shutil.which('g++') is None:
+        pytest.skip('g++ not available')
+    hdr = os.path.join(HERE, '..', 'pose_unsupervised_b200', 'csrc', 'lift_math.cuh')
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
+        subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-shared', '-fPIC', '-x', 'c++',
+                               '-o', SO, SRC])
+    return ctypes.CDLL(SO)
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_crop_affine_bit_exact(hc):
+    a = golden('affine.npz')
+    for i in np.where(a['rot'] == 0)[0]:
+        c = np.ascontiguousarray(a['center'][i:i + 1])
+        s = np.ascontiguousarray(a['scale'][i:i + 1])
+        if a['f32'][i]:
+            c, s = c.astype(np.float32), s.astype(np.float32)
+        for inv in (0, 1):
+            out = np.zeros(6)
+            hc.hc_crop_affine(P(c), int(c.dtype == np.float64), P(s), int(s.dtype == np.float64), 1,
+                              int(a['size'][i][0]), int(a['size'][i][1]), inv, P(out))
+            assert np.array_equal(out, a['inv' if inv else 'fwd'][i].ravel()), (i, inv)
+
+
+def test_project_h36m_vs_reference(hc):
+    c = golden('cameras.npz')
+    pts = np.ascontiguousarray(c['pts'])
+    for i, v in enumerate(c['cams']):
+        pk = np.zeros(24)
+        pk[:21] = v
+        out = np.zeros((len(pts), 2))
+        hc.hc_project(P(pk), P(pts), len(pts), 0, P(out))
+        # bit-exact on hosts whose BLAS accumulates R(x-T) with FMA; 1e-12 px otherwise
+        assert np.abs(out - c['proj'][i]).max() < 1e-10
+
+
+def test_unary_and_grid_vs_reference(hc):
+    r = golden('rpsm.npz')
+    for f in range(2):
+        hm = r['f%d_hm_q12' % f].astype(np.float32) / np.float32(4096)
+        grid = np.ascontiguousarray(r['f%d_grid0' % f])
+        g2 = np.zeros_like(grid)
+        hc.hc_grid(ctypes.c_double(2000.0), 16, P(np.ascontiguousarray(r['f%d_root' % f])), P(g2))
+        assert np.array_equal(g2, grid)
+        un = np.zeros((16, 4096))
+        for v in range(4):
+            pk = np.zeros(24)
+            pk[:21] = r['f%d_cams' % f][v]
+            aff = np.zeros(6)
+            cc = np.ascontiguousarray(r['f%d_box_center' % f][v:v + 1])
+            ss = np.ascontiguousarray(r['f%d_box_scale' % f][v:v + 1])
+            hc.hc_crop_affine(P(cc), 1, P(ss), 1, 1, 256, 256, 0, P(aff))
+            for j in range(16):
+                o = np.zeros(4096)
+                h = np.ascontiguousarray(hm[v, j])
+                hc.hc_unary(P(h), 64, 64, P(pk), P(aff), P(grid), 4096, ctypes.c_double(256.0),
+                            ctypes.c_double(256.0), P(o))
+                un[j] = un[j] + o
+        gu = r['f%d_unary0' % f]
+        assert np.abs(un - gu).max() <= 1e-12 * max(1.0, np.abs(gu).max())
+
+
+@pytest.mark.parametrize('nd', [0, 1])
+@pytest.mark.parametrize('noise', [0.0, 2.0, 30.0])
+def test_jacobi_dlt_vs_svd_oracle(hc, nd, noise):
+    """float64 Gram + Jacobi eigenvector against the oracle's SVD: budget 1e-2 mm (north_star)."""
+    rng = np.random.default_rng(0)
+    rigs = synth.camera_table(3, 4, seed=1)
+    poses = synth.random_poses(12, seed=2)
+    obs, cams = synth.multiview_observations(poses, rigs, rng.integers(0, 3, 12), noise_px=noise, seed=3,
+                                             distorted=not nd)
+    ref = otri.triangulate_poses(cams, obs, None, bool(nd))
+    worst = 0.0
+    for i in range(12):
+        pk = np.array([pack_camera(cams[i * 4 + v]) for v in range(4)])
+        for j in range(17):
+            xy = np.ascontiguousarray(obs[i * 4:(i + 1) * 4, j])
+            X = np.zeros(3)
+            assert hc.hc_triangulate(P(pk), P(xy), None, 4, nd, P(X)) == 4
+            worst = max(worst, np.linalg.norm(X - ref[i, j]))
+    assert worst < 1e-6
+
+
+def test_two_view_pairs_vs_svd_oracle(hc):
+    """RANSAC triangulates from pairs: the worst-conditioned use of the Gram matrix."""
+    rng = np.random.default_rng(1)
+    rigs = synth.camera_table(2, 4, seed=4)
+    poses = synth.random_poses(8, seed=5)
+    obs, cams = synth.multiview_observations(poses, rigs, rng.integers(0, 2, 8), noise_px=3.0, seed=6)
+    worst = 0.0
+    for i in range(8):
+        pk = np.array([pack_camera(cams[i * 4 + v]) for v in range(4)])
+        for a, b in [(0, 1), (0, 2), (1, 3), (2, 3)]:
+            vis = np.zeros((32, 17))
+            vis[i * 4 + a] = vis[i * 4 + b] = 1
+            ref = otri.triangulate_poses(cams, obs, vis)[i]
+            m = np.zeros(4, np.uint8)
+            m[a] = m[b] = 1
+            for j in range(0, 17, 4):
+                xy = np.ascontiguousarray(obs[i * 4:(i + 1) * 4, j])
+                X = np.zeros(3)
+                hc.hc_triangulate(P(pk), P(xy), P(m), 4, 0, P(X))
+                worst = max(worst, np.linalg.norm(X - ref[j]))
+    assert worst < 1e-5
