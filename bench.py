@@ -174,11 +174,11 @@ def run_reference_arm(args):
     steps = args.steps if args.steps else 3
     warmup = args.warmup if args.warmup is not None else 1
     steps, warmup = min(steps, 5), min(warmup, 2)        # bounded: each step is seconds of CPU work
-    per_worker = 16
     ctx = mp.get_context('fork')
     with ctx.Pool(cores) as pool:
-        for _ in range(warmup):
-            cpu_path_rate(2, cores, pool)
+        for _ in range(max(1, warmup)):
+            pilot = cpu_path_rate(4, cores, pool)           # also pays imports / page-in
+        per_worker = int(min(2048, max(8, pilot / cores * 6)))   # ~6 s of CPU work per step
         t0 = time.perf_counter()
         for _ in range(steps):
             cpu_path_rate(per_worker, cores, pool)
@@ -221,6 +221,9 @@ def run_ours(args):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
+    if args.lift_variant is not None:
+        from pose_unsupervised_b200 import _lib
+        _lib.call('pb200_set_tuning', 1, args.lift_variant)
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
@@ -322,7 +325,7 @@ def run_ours(args):
                     'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps,
                     'api': 'pose_unsupervised_b200.multiviews.triangulate.lift_heatmaps (numpy in, numpy out)'},
             'gpu_launches': steps * launches_per_step,
-            'roofline': {'bound': 'hbm', 'kernel': 'lift_fused_kernel', 'achieved': achieved, 'peak': peak,
+            'roofline': {'bound': 'hbm', 'kernel': 'lift_fused_kernel' if args.lift_variant == 0 else 'lift_fused_tma_kernel', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                          'peak_source': peak_src, 'kernel_ms': kern_ms,
                          'algorithmic_bytes_per_launch': B * BYTES_PER_FRAME},
@@ -349,8 +352,9 @@ def cpu_baseline_leg():
     os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
     import multiprocessing as mp
     cores = host_cores()
-    one = cpu_path_rate(8, 1)                                  # pilot, also the per-core number
-    per_worker = int(min(64, max(4, one * 12)))                # ~12 s per process
+    cpu_path_rate(1, 1)                                        # imports, page-in
+    one = cpu_path_rate(16, 1)                                 # pilot, also the per-core number
+    per_worker = int(min(4096, max(8, one * 12)))              # ~12 s per process
     ctx = mp.get_context('fork')
     with ctx.Pool(cores) as pool:
         rate = cpu_path_rate(per_worker, cores, pool)
@@ -425,6 +429,7 @@ def main():
     ap.add_argument('--workload', default='lift', choices=['lift', 'rpsm'])
     ap.add_argument('--frames', type=int, default=4096, help='frames per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--lift-variant', type=int, default=None, help='0 = LDG front end, 1 = TMA ring (default)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

@@ -161,20 +161,26 @@ int pb200_mpjpe_stats(const double* pred, const double* gt, int B, int J, double
  * the warp that finishes the last map of a frame lifts that frame.
  *   conf_thre : a joint is visible in a view iff maxval > conf_thre
  *               (run/test/test_pseudo_label.py:194); pass use_conf = 0 for "all visible"
- *   workspace : int32 [pb200_lift_workspace_ints(B)] zero-initialised once by the
- *               caller; the kernel leaves it zeroed.
+ *   workspace : pb200_lift_workspace_bytes(B, V, J) bytes, 16-byte aligned, zero-initialised
+ *               once by the caller; the kernel leaves it all-zero (arrival counters and the
+ *               16-byte hand-off records, see csrc/lift_fused.cu).
  *   outputs   : out_xy/out_maxval/out_idx as pb200_decode; out_X [B,J,3] float64;
- *               out_err [B*V,J] float32 reprojection error in pixels (NaN-free zeros
- *               where the joint was not lifted); out_proj [B*V,J,2] float64 or NULL.
+ *               out_err [B*V,J] float32 reprojection error in pixels (zeros where the joint
+ *               was not lifted); out_proj [B*V,J,2] float64 or NULL.
  */
-size_t pb200_lift_workspace_ints(int B);
+size_t pb200_lift_workspace_bytes(int B, int V, int J);
 int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, int B, int V, int J, int H, int W,
                      const double* affine, int post_process,
                      const double* campack, const int32_t* cam_index, int no_distortion,
                      int use_conf, float conf_thre,
                      float* out_xy, float* out_maxval, int32_t* out_idx,
                      double* out_X, float* out_err, double* out_proj,
-                     int32_t* workspace, void* stream);
+                     void* workspace, void* stream);
+
+/* Tuning hook (process-wide).  PB200_TUNE_LIFT_VARIANT: streaming front end of
+ * pb200_lift_fused, 0 = LDG.128, 1 = per-warp TMA bulk-copy ring (default). */
+#define PB200_TUNE_LIFT_VARIANT 1
+int pb200_set_tuning(int key, int value);
 
 /* ---- RPSM: recursive pictorial structure grid search -------------------------------
  * Replaces multiviews.pictorial.rpsm (lib/multiviews/pictorial.py:214-250) for a

@@ -40,7 +40,8 @@ _PROTOS = {
     'pb200_epipolar': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                c_int, c_void_p, c_void_p, c_void_p]),
     'pb200_mpjpe_stats': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    'pb200_lift_workspace_ints': (c_size_t, [c_int]),
+    'pb200_lift_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'pb200_set_tuning': (c_int, [c_int, c_int]),
     'pb200_lift_fused': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                  c_void_p, c_void_p, c_int, c_int, c_float,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

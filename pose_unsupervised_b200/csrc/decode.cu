@@ -83,11 +83,11 @@ extern "C" int pb200_decode(const float* const* hm_views_host, int n_ptr, int N,
                             int32_t* out_idx, void* stream) {
   PB_REQUIRE(N >= 0 && J >= 1 && H >= 1 && W >= 1, "bad shape N=%d J=%d H=%d W=%d", N, J, H, W);
   PB_REQUIRE((long long)H * W < (1LL << 24), "map of %dx%d exceeds the float32-exact index range", H, W);
+  if (N == 0) return PB200_OK;
   PB_REQUIRE(out_xy && out_maxval, "null output");
   HmViews hv;
   int rc = fill_views(hm_views_host, n_ptr, N, hv);
   if (rc != PB200_OK) return rc;
-  if (N == 0) return PB200_OK;
   const long long maps = (long long)N * J;
   const int sm = cached_sm_count();
   if (sm <= 0) return PB200_ERR_CUDA;

@@ -125,32 +125,43 @@ struct DecodeOut {
   int idx;
 };
 
-// Whole-warp decode of one map; every lane returns the same result.
-__device__ __forceinline__ DecodeOut decode_map(const float* __restrict__ base, int H, int W, bool vec_ok,
-                                                const double* __restrict__ trans /* 6 or null */,
-                                                bool post_process, int lane) {
-  const int hw = H * W;
+// Whole-warp flat argmax of one map straight from global memory; every lane gets the result.
+__device__ __forceinline__ ArgMax scan_map(const float* __restrict__ base, int hw, bool vec_ok, int lane) {
   float best;
   int bidx;
-  ArgMax am;
   bool need_exact = !vec_ok;
   if (vec_ok) {
     bool saw_nan;
     scan_map_vec4(base, hw >> 2, lane, best, bidx, saw_nan);
     need_exact = __any_sync(0xffffffffu, saw_nan);
-    if (!need_exact) am = warp_argmax<false>(best, bidx);
+    if (!need_exact) return warp_argmax<false>(best, bidx);
   }
-  if (need_exact) {
-    scan_map_exact(base, hw, lane, best, bidx);
-    am = warp_argmax<true>(best, bidx);
-  }
+  scan_map_exact(base, hw, lane, best, bidx);
+  return warp_argmax<true>(best, bidx);
+}
+
+struct Affine6 {
+  double t[6];
+};
+
+__device__ __forceinline__ Affine6 load_affine(const double* __restrict__ trans) {
+  Affine6 a;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) a.t[k] = __ldg(trans + k);
+  return a;
+}
+
+// Coordinates from the argmax: mask, quarter-pixel shift, inverse crop affine.
+__device__ __forceinline__ DecodeOut finish_map(const ArgMax am, const float* __restrict__ base, int H,
+                                                int W, bool has_trans, const Affine6& a,
+                                                bool post_process) {
   DecodeOut o;
   o.idx = am.idx;
   o.maxval = am.val;
   float fx = (float)(am.idx % W);
   float fy = (float)(am.idx / W);
   if (!(am.val > 0.0f)) { fx = 0.0f; fy = 0.0f; }  // pred_mask (inference.py:43-46)
-  if (trans != nullptr) {
+  if (has_trans) {
     if (post_process) {
       const int px = (int)floorf(fx + 0.5f), py = (int)floorf(fy + 0.5f);
       if (1 < px && px < W - 1 && 1 < py && py < H - 1) {
@@ -166,14 +177,24 @@ __device__ __forceinline__ DecodeOut decode_map(const float* __restrict__ base, 
     }
     // [x, y, 1] @ trans.T in float64 (BLAS accumulation order), stored float32
     const double dxx = (double)fx, dyy = (double)fy;
-    const double ox = fma(dyy, trans[1], dxx * trans[0]) + trans[2];
-    const double oy = fma(dyy, trans[4], dxx * trans[3]) + trans[5];
+    const double ox = fma(dyy, a.t[1], dxx * a.t[0]) + a.t[2];
+    const double oy = fma(dyy, a.t[4], dxx * a.t[3]) + a.t[5];
     fx = (float)ox;
     fy = (float)oy;
   }
   o.x = fx;
   o.y = fy;
   return o;
+}
+
+// Whole-warp decode of one map; every lane returns the same result.
+__device__ __forceinline__ DecodeOut decode_map(const float* __restrict__ base, int H, int W, bool vec_ok,
+                                                const double* __restrict__ trans /* 6 or null */,
+                                                bool post_process, int lane) {
+  Affine6 a;
+  if (trans != nullptr) a = load_affine(trans);  // issued before the scan: its latency is hidden
+  const ArgMax am = scan_map(base, H * W, vec_ok, lane);
+  return finish_map(am, base, H, W, trans != nullptr, a, post_process);
 }
 
 }  // namespace pb200

@@ -3,23 +3,41 @@
 // BASELINE.json config 2 (B frames x V views x J joints of HxW float32 heatmaps).
 // The only large operand is the heatmap tensor; it is streamed once by
 // warp-per-map decoders (csrc/decode.cuh).  Lifting a frame needs the V*J decoded
-// coordinates of that frame, which live in 8*V*J bytes of L2-resident output, so
-// instead of a second launch the warp that completes the LAST map of a frame lifts
-// that frame in place: lanes = joints, float64 DLT + Jacobi per lane
-// (csrc/lift.cuh), reprojection error per view.
+// coordinates of that frame (16*V*J bytes, L2 resident), so instead of a second
+// launch the warp that completes the LAST map of a frame lifts that frame in
+// place: lanes = joints, float64 DLT + Jacobi per lane (csrc/lift.cuh),
+// reprojection error per view.
 //
-// Scheduling: persistent blocks (a whole number per SM), warps pull map indices
-// from a global counter, so a warp that is busy lifting simply pulls fewer maps and
-// the HBM stream never waits for it.  A per-frame arrival counter (release: decoded
-// outputs -> __threadfence -> atomicAdd; acquire: atomicAdd -> __threadfence ->
-// ld.cg) finds the completing warp.  All counters are left at zero on exit, so the
-// workspace needs zeroing only once.
+// Scheduling: persistent blocks (a whole number per SM); warps pull map indices
+// from a global counter (the next claim is issued before the current map is
+// scanned, so its round trip is hidden), so a warp that is busy lifting simply
+// pulls fewer maps and the HBM stream never waits for it.
+//
+// Hand-off without memory fences: a decoder publishes its result as ONE 16-byte
+// record {x, y, maxval, tag=1} (a single st.global.v4) and then bumps the frame's
+// arrival counter with a relaxed atomic.  The warp that sees the last arrival reads
+// the V*J records with volatile loads; a record whose tag is still 0 is simply
+// re-read -- its store was issued before the counter was bumped, so it is already
+// in flight and the wait does not depend on any other warp being scheduled.  The
+// lifter zeroes the tags again, the last block out resets the claim counter: the
+// workspace is all-zero after every launch.  (The first version used
+// __threadfence() + atomicAdd per map; ncu showed 35 % of all stall cycles on
+// MEMBAR, see profiles/.)
+//
+// Two streaming front ends, same arithmetic:
+//   variant 0  LDG.128 (ld.global.nc.L1::no_allocate), 8 loads per lane per iteration
+//   variant 1  per-warp ring of 4 KiB cp.async.bulk (TMA) chunks in shared memory with
+//              mbarrier completion; the copy engine keeps kStages chunks per warp in
+//              flight independently of the warp's registers and of its epilogue.
 #include "decode.cuh"
 #include "lift.cuh"
 
 namespace pb200 {
 
 constexpr int kFusedWarps = 8;
+constexpr int kChunkFloats = 1024;                  // 4 KiB per bulk copy
+constexpr int kChunkBytes = kChunkFloats * 4;
+constexpr int kStages = 3;                          // 8 warps x 3 x 4 KiB = 96 KiB per block, 2 blocks per SM
 
 struct FusedParams {
   HmViews hv;
@@ -38,16 +56,23 @@ struct FusedParams {
   double* out_X;
   float* out_err;
   double* out_proj;
-  int32_t* ws;  // [0] next map, [1] finished blocks, [2 + f] maps decoded of frame f
+  int32_t* ws;     // [0] next map, [1] finished blocks, [4 + f] maps decoded of frame f
+  float4* records; // [B*V*J] {x, y, maxval, tag}
 };
 
-struct FusedXY {
-  const float2* xy;  // &out_xy[frame*V, j]
-  int row_stride;    // J
+struct RecordXY {
+  const float4* rec;  // &records[frame*V*J + j]
+  int row_stride;     // J
+  __device__ __forceinline__ float4 get(int v) const {
+    const float4* p = rec + (size_t)v * row_stride;
+    float4 r = __ldcv(p);
+    while (__float_as_int(r.w) == 0) r = __ldcv(p);  // store already in flight, see header
+    return r;
+  }
   __device__ __forceinline__ void operator()(int v, double& x, double& y) const {
-    const float2 q = __ldcg(xy + (size_t)v * row_stride);
-    x = (double)q.x;
-    y = (double)q.y;
+    const float4 r = get(v);
+    x = (double)r.x;
+    y = (double)r.y;
   }
 };
 
@@ -55,12 +80,11 @@ __device__ __noinline__ void lift_frame_joint(const FusedParams& p, int f, int j
   const int V = p.V, J = p.J;
   const size_t row0 = (size_t)f * V;
   const int32_t* cam_row = p.cam_index + row0;
-  FusedXY xy{reinterpret_cast<const float2*>(p.out_xy) + row0 * J + j, J};
+  RecordXY xy{p.records + row0 * J + j, J};
   uint32_t mask = 0u;
   for (int v = 0; v < V; ++v) {
-    bool on = true;
-    if (p.use_conf) on = __ldcg(p.out_maxval + (row0 + v) * J + j) > p.conf_thre;
-    if (on) mask |= 1u << v;
+    const float4 r = xy.get(v);  // also makes sure every record of this joint has landed
+    if (!p.use_conf || r.z > p.conf_thre) mask |= 1u << v;
   }
   const bool nd = p.no_dist != 0;
   double X[3];
@@ -74,38 +98,30 @@ __device__ __noinline__ void lift_frame_joint(const FusedParams& p, int f, int j
     p.out_err[o] = (float)e;
     if (p.out_proj) { p.out_proj[2 * o] = pu; p.out_proj[2 * o + 1] = pv; }
   }
+  for (int v = 0; v < V; ++v)  // leave the workspace clean for the next launch
+    p.records[(row0 + v) * J + j] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-__global__ void __launch_bounds__(kFusedWarps * 32, 4) lift_fused_kernel(const FusedParams p) {
-  const int lane = threadIdx.x & 31;
-  const int J = p.J, V = p.V, HW = p.H * p.W;
-  const int per_frame = V * J;
-  const int total = p.B * per_frame;
-  for (;;) {
-    int m = 0;
-    if (lane == 0) m = atomicAdd(p.ws, 1);
-    m = __shfl_sync(0xffffffffu, m, 0);
-    if (m >= total) break;
-    const int row = m / J, j = m - row * J;
-    const float* base = map_base(p.hv, row, j, J, HW);
-    const DecodeOut o = decode_map(base, p.H, p.W, p.vec_ok != 0, p.affine + 6 * (size_t)row,
-                                   p.post_process != 0, lane);
-    int last = 0;
-    const int f = row / V;
-    if (lane == 0) {
-      reinterpret_cast<float2*>(p.out_xy)[m] = make_float2(o.x, o.y);
-      p.out_maxval[m] = o.maxval;
-      if (p.out_idx) p.out_idx[m] = o.idx;
-      __threadfence();  // release the decoded outputs
-      last = atomicAdd(p.ws + 2 + f, 1) == per_frame - 1;
-    }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
-      __threadfence();  // acquire the other warps' outputs
-      for (int jj = lane; jj < J; jj += 32) lift_frame_joint(p, f, jj);
-      if (lane == 0) p.ws[2 + f] = 0;  // leave the workspace clean
-    }
+// lane 0 publishes one decoded map; returns (to every lane) whether it was the frame's last
+__device__ __forceinline__ bool publish(const FusedParams& p, int m, int f, const DecodeOut& o, int lane) {
+  int last = 0;
+  if (lane == 0) {
+    reinterpret_cast<float2*>(p.out_xy)[m] = make_float2(o.x, o.y);
+    p.out_maxval[m] = o.maxval;
+    if (p.out_idx) p.out_idx[m] = o.idx;
+    p.records[m] = make_float4(o.x, o.y, o.maxval, __int_as_float(1));
+    last = atomicAdd(p.ws + 4 + f, 1) == p.V * p.J - 1;
   }
+  return __shfl_sync(0xffffffffu, last, 0) != 0;
+}
+
+__device__ __forceinline__ void lift_if_last(const FusedParams& p, bool last, int f, int lane) {
+  if (!last) return;
+  for (int jj = lane; jj < p.J; jj += 32) lift_frame_joint(p, f, jj);
+  if (lane == 0) p.ws[4 + f] = 0;
+}
+
+__device__ __forceinline__ void block_exit(const FusedParams& p) {
   __syncthreads();
   if (threadIdx.x == 0) {
     if (atomicAdd(p.ws + 1, 1) == (int)gridDim.x - 1) {  // last block out resets the counters
@@ -115,15 +131,196 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 4) lift_fused_kernel(const F
   }
 }
 
+__device__ __forceinline__ int claim(const FusedParams& p, int lane) {
+  int m = 0;
+  if (lane == 0) m = atomicAdd(p.ws, 1);
+  return m;  // valid in lane 0 only until broadcast
+}
+
+// ---- variant 0: LDG front end ----------------------------------------------------------
+__global__ void __launch_bounds__(kFusedWarps * 32, 4) lift_fused_kernel(const FusedParams p) {
+  const int lane = threadIdx.x & 31;
+  const int J = p.J, V = p.V, HW = p.H * p.W;
+  const int total = p.B * V * J;
+  int m = __shfl_sync(0xffffffffu, claim(p, lane), 0);
+  while (m < total) {
+    const int next_raw = claim(p, lane);  // in flight while this map is scanned
+    const int row = m / J, j = m - row * J;
+    const float* base = map_base(p.hv, row, j, J, HW);
+    const DecodeOut o = decode_map(base, p.H, p.W, p.vec_ok != 0, p.affine + 6 * (size_t)row,
+                                   p.post_process != 0, lane);
+    const int f = row / V;
+    lift_if_last(p, publish(p, m, f, o, lane), f, lane);
+    m = __shfl_sync(0xffffffffu, next_raw, 0);
+  }
+  block_exit(p);
+}
+
+// ---- variant 1: TMA bulk-copy ring front end ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct MapCursor {
+  int m;              // claimed map index (>= total: none)
+  const float* base;  // its first element
+  int issued;         // chunks handed to the copy engine so far
+};
+
+__global__ void __launch_bounds__(kFusedWarps * 32, 2) lift_fused_tma_kernel(const FusedParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * kStages * kChunkFloats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kFusedWarps * kStages * kChunkBytes) +
+                   warp * kStages;
+  const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars);
+  if (lane == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(bars_s + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int J = p.J, V = p.V, H = p.H, W = p.W, HW = H * W;
+  const int total = p.B * V * J;
+  const int nchunk = (HW + kChunkFloats - 1) / kChunkFloats;
+  const int last_floats = HW - (nchunk - 1) * kChunkFloats;
+  unsigned q_issue = 0, q_cons = 0;  // chunk sequence numbers of this warp (stage = q % kStages)
+
+  auto set_map = [&](MapCursor& c, int m) {
+    c.m = m;
+    c.issued = 0;
+    c.base = nullptr;
+    if (m < total) {
+      const int row = m / J;
+      c.base = map_base(p.hv, row, m - row * J, J, HW);
+    }
+  };
+  // hand the next chunk of `c` to the copy engine (lane 0 issues; cursors are warp-uniform)
+  auto issue = [&](MapCursor& c) {
+    const int k = c.issued;
+    const uint32_t bytes = (k == nchunk - 1 ? last_floats : kChunkFloats) * 4;
+    const unsigned s = q_issue % kStages;
+    if (lane == 0) {
+      mbar_expect_tx(bars_s + 8 * s, bytes);
+      bulk_g2s(ring_s + s * kChunkBytes, c.base + (size_t)k * kChunkFloats, bytes, bars_s + 8 * s);
+    }
+    ++c.issued;
+    ++q_issue;
+  };
+
+  MapCursor cur, nxt;
+  set_map(cur, __shfl_sync(0xffffffffu, claim(p, lane), 0));
+  set_map(nxt, total);
+  bool nxt_claimed = false;
+  // keep the ring full: chunks of the current map first, then of the next claimed map
+  auto top_up = [&]() {
+    while (q_issue - q_cons < (unsigned)kStages) {
+      if (cur.m < total && cur.issued < nchunk) { issue(cur); continue; }
+      if (!nxt_claimed) {
+        set_map(nxt, __shfl_sync(0xffffffffu, claim(p, lane), 0));
+        nxt_claimed = true;
+      }
+      if (nxt.m < total && nxt.issued < nchunk) { issue(nxt); continue; }
+      break;
+    }
+  };
+
+  while (cur.m < total) {
+    const int m = cur.m, row = m / J;
+    const Affine6 aff = load_affine(p.affine + 6 * (size_t)row);
+    float best = -INFINITY;
+    int bidx = 4 * lane < HW ? 4 * lane : 0x7fffffff;
+    bool nanp = false;
+    for (int k = 0; k < nchunk; ++k) {
+      top_up();
+      const unsigned s = q_cons % kStages;
+      mbar_wait(bars_s + 8 * s, (q_cons / kStages) & 1u);
+      const float4* src = reinterpret_cast<const float4*>(ring + s * kChunkFloats);
+      const int nvec = (k == nchunk - 1 ? last_floats : kChunkFloats) >> 2;
+      const int e0 = k * kChunkFloats + 4 * lane;
+#pragma unroll
+      for (int u = 0; u < kChunkFloats / 128; ++u) {
+        const int vi = u * 32 + lane;
+        if (vi < nvec) {
+          const float4 q = src[vi];
+          const int e = e0 + 128 * u;
+          nanp |= (q.x != q.x) | (q.y != q.y) | (q.z != q.z) | (q.w != q.w);
+          if (q.x > best) { best = q.x; bidx = e; }
+          if (q.y > best) { best = q.y; bidx = e + 1; }
+          if (q.z > best) { best = q.z; bidx = e + 2; }
+          if (q.w > best) { best = q.w; bidx = e + 3; }
+        }
+      }
+      __syncwarp();  // every lane is done with stage s before it is refilled
+      ++q_cons;
+    }
+    top_up();  // the next map's first chunks fly while this one is finished
+    ArgMax am;
+    if (__any_sync(0xffffffffu, nanp)) {  // rare: exact numpy NaN rules, re-read from L2
+      scan_map_exact(cur.base, HW, lane, best, bidx);
+      am = warp_argmax<true>(best, bidx);
+    } else {
+      am = warp_argmax<false>(best, bidx);
+    }
+    const DecodeOut o = finish_map(am, cur.base, H, W, true, aff, p.post_process != 0);
+    const int f = row / V;
+    lift_if_last(p, publish(p, m, f, o, lane), f, lane);
+    if (!nxt_claimed) {
+      set_map(nxt, __shfl_sync(0xffffffffu, claim(p, lane), 0));
+    }
+    cur = nxt;
+    set_map(nxt, total);
+    nxt_claimed = false;
+  }
+  block_exit(p);
+}
+
 int fill_views(const float* const* hm_views_host, int n_ptr, int N, HmViews& hv);
 bool views_vec_ok(const HmViews& hv, int HW);
+
+static int g_lift_variant = 1;
 
 }  // namespace pb200
 
 using namespace pb200;
 
-extern "C" size_t pb200_lift_workspace_ints(int B) {
-  return (size_t)(B < 0 ? 0 : B) + 4;
+extern "C" int pb200_set_tuning(int key, int value) {
+  PB_REQUIRE(key == PB200_TUNE_LIFT_VARIANT, "unknown tuning key %d", key);
+  PB_REQUIRE(value == 0 || value == 1, "lift variant must be 0 (LDG) or 1 (TMA ring)");
+  g_lift_variant = value;
+  return PB200_OK;
+}
+
+extern "C" size_t pb200_lift_workspace_bytes(int B, int V, int J) {
+  if (B < 0 || V < 0 || J < 0) return 0;
+  const size_t ints = (((size_t)B + 4 + 3) / 4) * 4;  // keeps the records 16-byte aligned
+  return ints * 4 + (size_t)B * V * J * 16;
 }
 
 extern "C" int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, int B, int V, int J,
@@ -131,18 +328,19 @@ extern "C" int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, in
                                 const double* campack, const int32_t* cam_index, int no_distortion,
                                 int use_conf, float conf_thre, float* out_xy, float* out_maxval,
                                 int32_t* out_idx, double* out_X, float* out_err, double* out_proj,
-                                int32_t* workspace, void* stream) {
+                                void* workspace, void* stream) {
   PB_REQUIRE(B >= 0 && J >= 1 && H >= 1 && W >= 1, "bad shape B=%d J=%d H=%d W=%d", B, J, H, W);
+  if (B == 0) return PB200_OK;
   PB_REQUIRE(V >= 2 && V <= PB200_MAX_VIEWS, "V=%d outside [2,%d]", V, PB200_MAX_VIEWS);
   PB_REQUIRE((long long)H * W < (1LL << 24), "map of %dx%d exceeds the float32-exact index range", H, W);
-  PB_REQUIRE((long long)B * V * J < (1LL << 31) - 65536, "B*V*J too large for one launch; split the batch");
+  PB_REQUIRE((long long)B * V * J < (1LL << 31) - (1 << 20), "B*V*J too large for one launch; split the batch");
   PB_REQUIRE(affine && campack && cam_index, "null input pointer");
   PB_REQUIRE(out_xy && out_maxval && out_X && out_err && workspace, "null output / workspace pointer");
+  PB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "workspace must be 16-byte aligned");
   PB_REQUIRE(n_ptr == 1 || n_ptr == V, "n_ptr must be 1 or V");
   FusedParams p;
   int rc = fill_views(hm_views_host, n_ptr, B * V, p.hv);
   if (rc != PB200_OK) return rc;
-  if (B == 0) return PB200_OK;
   p.B = B; p.V = V; p.J = J; p.H = H; p.W = W;
   p.vec_ok = views_vec_ok(p.hv, H * W) ? 1 : 0;
   p.affine = affine; p.post_process = post_process;
@@ -150,19 +348,37 @@ extern "C" int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, in
   p.use_conf = use_conf; p.conf_thre = conf_thre;
   p.out_xy = out_xy; p.out_maxval = out_maxval; p.out_idx = out_idx;
   p.out_X = out_X; p.out_err = out_err; p.out_proj = out_proj;
-  p.ws = workspace;
-  static int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    int n = 0;
-    PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lift_fused_kernel, kFusedWarps * 32, 0));
-    blocks_per_sm = n > 0 ? n : 1;
-  }
+  p.ws = reinterpret_cast<int32_t*>(workspace);
+  const size_t ints = (((size_t)B + 4 + 3) / 4) * 4;
+  p.records = reinterpret_cast<float4*>(p.ws + ints);
   const int sm = cached_sm_count();
   if (sm <= 0) return PB200_ERR_CUDA;
-  long long blocks = (long long)sm * blocks_per_sm;
   const long long need = ((long long)B * V * J + kFusedWarps - 1) / kFusedWarps;
-  if (blocks > need) blocks = need;
-  lift_fused_kernel<<<(unsigned)blocks, kFusedWarps * 32, 0, (cudaStream_t)stream>>>(p);
-  PB_LAUNCH_CHECK("lift_fused_kernel");
+  const bool tma = g_lift_variant == 1 && p.vec_ok;  // bulk copies need 16-byte aligned maps
+  if (tma) {
+    const size_t smem = (size_t)kFusedWarps * kStages * kChunkBytes + (size_t)kFusedWarps * kStages * 8;
+    static int blocks_per_sm_tma = 0;
+    if (blocks_per_sm_tma == 0) {
+      PB_CUDA(cudaFuncSetAttribute(lift_fused_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int n = 0;
+      PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lift_fused_tma_kernel, kFusedWarps * 32, smem));
+      blocks_per_sm_tma = n > 0 ? n : 1;
+    }
+    long long blocks = (long long)sm * blocks_per_sm_tma;
+    if (blocks > need) blocks = need;
+    lift_fused_tma_kernel<<<(unsigned)blocks, kFusedWarps * 32, smem, (cudaStream_t)stream>>>(p);
+    PB_LAUNCH_CHECK("lift_fused_tma_kernel");
+  } else {
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+      int n = 0;
+      PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lift_fused_kernel, kFusedWarps * 32, 0));
+      blocks_per_sm = n > 0 ? n : 1;
+    }
+    long long blocks = (long long)sm * blocks_per_sm;
+    if (blocks > need) blocks = need;
+    lift_fused_kernel<<<(unsigned)blocks, kFusedWarps * 32, 0, (cudaStream_t)stream>>>(p);
+    PB_LAUNCH_CHECK("lift_fused_kernel");
+  }
   return PB200_OK;
 }

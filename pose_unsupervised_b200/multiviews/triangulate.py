@@ -124,7 +124,7 @@ def lift_heatmaps(heatmaps, center, scale, camera_params, nviews=4, post_process
     poses3d = rt.empty((B, J, 3), torch.float64)
     err = rt.empty((N, J), torch.float32)
     proj = rt.empty((N, J, 2), torch.float64) if return_proj else None
-    ws = rt.workspace('lift', 4 * _lib.load().pb200_lift_workspace_ints(B))
+    ws = rt.workspace('lift', _lib.load().pb200_lift_workspace_bytes(B, nviews, J))
     ptrs = (ctypes.c_void_p * len(views))(*[v.data_ptr() for v in views])
     _lib.call('pb200_lift_fused', ptrs, len(views), B, nviews, J, H, W, rt.ptr(affine),
               int(bool(post_process)), rt.ptr(table.pack), rt.ptr(table.index),

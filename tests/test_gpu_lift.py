@@ -59,6 +59,7 @@ def test_fused_confidence_threshold_and_unfused_agree():
     B, V, J = 40, 4, 17
     hm, center, scale, cams = _inputs(B, V, J, 64, seed=5)
     hm[::5] *= 0.3                                                    # some rows below the threshold
+    hm[:12] *= 0.3                                                    # and three whole frames
     thre = 0.6
     res = lift_heatmaps(hm, center, scale, cams, conf_thre=thre, return_proj=True)
     xy, mv = decode_heatmaps(hm, center, scale, post_process=True)
@@ -71,6 +72,30 @@ def test_fused_confidence_threshold_and_unfused_agree():
     ref = otri.triangulate_poses(cams, xy.cpu().numpy(), ovis)
     assert np.abs(res.poses3d.cpu().numpy() - ref).max() < 1e-2
     assert (ref == 0).all(axis=2).any()                               # some joints had < 2 views
+
+
+@pytest.mark.parametrize('variant', [0, 1])
+def test_fused_front_ends_agree(variant):
+    """LDG and TMA-ring front ends are the same arithmetic: identical bits, incl. NaN maps and 80x80."""
+    from pose_unsupervised_b200 import _lib
+    from pose_unsupervised_b200.multiviews.triangulate import lift_heatmaps
+    try:
+        _lib.call('pb200_set_tuning', 1, variant)
+        for hw in (64, 80, 32):
+            hm, center, scale, cams = _inputs(16, 4, 17, hw, seed=hw)
+            hm[3, 2, 5, 7] = np.nan
+            hm[9, 0] = -1.0
+            res = lift_heatmaps(hm, center, scale, cams, return_idx=True).numpy()
+            assert np.array_equal(res.idx, oinf.flat_argmax(hm)), (variant, hw)
+            rp, rm = oinf.get_final_preds(True, hm, center, scale)
+            assert np.array_equal(res.maxvals, rm[:, :, 0], equal_nan=True)
+            assert ulp_diff_f32(res.xy, rp).max() <= 1
+            ok = ~np.isnan(res.xy).any(axis=2)
+            pts = otri.triangulate_poses(cams, np.nan_to_num(res.xy), ok)
+            good = ok.reshape(16, 4, 17).all(axis=1)
+            assert np.abs(res.poses3d - pts)[good].max() < 1e-2
+    finally:
+        _lib.call('pb200_set_tuning', 1, 1)
 
 
 def test_fused_repeated_launches_leave_workspace_clean():
