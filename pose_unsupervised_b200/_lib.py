@@ -7,7 +7,8 @@ import ctypes
 import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_size_t, c_void_p
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libposeb200.so')
+LIB_PATH = os.environ.get('PB200_LIB',   # override used by tuning sweeps only
+                          os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libposeb200.so'))
 
 F32, F64 = 0, 1
 MAX_VIEWS = 8

@@ -11,7 +11,7 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
-LIB_PATH = os.path.join(PKG_DIR, 'libposeb200.so')
+LIB_PATH = os.environ.get('PB200_LIB', os.path.join(PKG_DIR, 'libposeb200.so'))   # PB200_LIB: tuning sweeps only
 SOURCES = ['api.cu', 'decode.cu', 'geometry.cu', 'lift_fused.cu', 'rpsm.cu']
 HEADERS = ['pb_common.cuh', 'lift_math.cuh', 'decode.cuh', 'lift.cuh',
            os.path.join('..', '..', 'include', 'poseb200.h')]
@@ -39,7 +39,8 @@ def build(force=False, verbose=False):
     """Compile every CUDA source into pose_unsupervised_b200/libposeb200.so."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
+    extra = os.environ.get('PB200_NVCC_EXTRA', '').split()           # e.g. -DPB_STAGES=4 (tuning sweeps)
+    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + \
         ['-o', LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:

@@ -34,6 +34,37 @@ decode_kernel(HmViews hv, int N, int J, int H, int W, int vec_ok,
   }
 }
 
+// Same decode with the TMA ring front end (decode.cuh::stream_maps_tma); warps take maps
+// blockIdx*8+warp, +gridDim*8, ... so no claim counter is needed.
+__global__ void __launch_bounds__(kDecodeWarps * 32, 2)
+decode_tma_kernel(HmViews hv, int N, int J, int H, int W, const double* __restrict__ affine,
+                  int post_process, float* __restrict__ out_xy, float* __restrict__ out_maxval,
+                  int32_t* __restrict__ out_idx) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long total_ll = (long long)N * J;
+  const int total = (int)total_ll;
+  const long long stride = (long long)gridDim.x * kDecodeWarps;
+  long long next = (long long)blockIdx.x * kDecodeWarps + warp;
+  Affine6 aff;
+  stream_maps_tma(
+      smem_raw, kDecodeWarps, hv, J, H * W, total,
+      [&]() {
+        const long long m = next;
+        next += stride;
+        return m < total_ll ? (int)m : total;
+      },
+      [&](int m) { if (affine) aff = load_affine(affine + 6 * (size_t)(m / J)); },
+      [&](int m, const float* base, ArgMax am) {
+        const DecodeOut o = finish_map(am, base, H, W, affine != nullptr, aff, post_process != 0);
+        if (lane == 0) {
+          reinterpret_cast<float2*>(out_xy)[m] = make_float2(o.x, o.y);
+          out_maxval[m] = o.maxval;
+          if (out_idx) out_idx[m] = o.idx;
+        }
+      });
+}
+
 __global__ void crop_affine_kernel(const void* center, int c_f64, const void* scale, int s_f64, int n,
                                    int out_w, int out_h, int inv, double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,6 +122,24 @@ extern "C" int pb200_decode(const float* const* hm_views_host, int n_ptr, int N,
   const long long maps = (long long)N * J;
   const int sm = cached_sm_count();
   if (sm <= 0) return PB200_ERR_CUDA;
+  PB_REQUIRE(maps < (1LL << 31) - (1 << 20), "N*J too large for one launch; split the batch");
+  if (views_vec_ok(hv, H * W)) {  // TMA ring front end
+    const size_t smem = tma_ring_smem_bytes(kDecodeWarps);
+    static int blocks_per_sm_tma = 0;
+    if (blocks_per_sm_tma == 0) {
+      PB_CUDA(cudaFuncSetAttribute(decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int n = 0;
+      PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, decode_tma_kernel, kDecodeWarps * 32, smem));
+      blocks_per_sm_tma = n > 0 ? n : 1;
+    }
+    long long blocks = (maps + kDecodeWarps - 1) / kDecodeWarps;
+    const long long cap = (long long)sm * blocks_per_sm_tma;
+    if (blocks > cap) blocks = cap;
+    decode_tma_kernel<<<(unsigned)blocks, kDecodeWarps * 32, smem, (cudaStream_t)stream>>>(
+        hv, N, J, H, W, affine, post_process, out_xy, out_maxval, out_idx);
+    PB_LAUNCH_CHECK("decode_tma_kernel");
+    return PB200_OK;
+  }
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
     int n = 0;

@@ -197,5 +197,182 @@ __device__ __forceinline__ DecodeOut decode_map(const float* __restrict__ base, 
   return finish_map(am, base, H, W, trans != nullptr, a, post_process);
 }
 
+// ---------------------------------------------------------------------------
+// TMA front end: every warp owns a ring of kStages x 4 KiB in shared memory that the
+// copy engine fills with cp.async.bulk (SASS: UBLKCP) and signals through an mbarrier
+// per stage.  The warp that consumes a stage re-arms it with the next chunk of its
+// current map or, once that is fully issued, of its NEXT map, so kStages chunks per
+// warp stay in flight across map boundaries and across the per-map epilogue,
+// independent of registers.  Needs 16-byte aligned maps with H*W % 4 == 0.
+// ---------------------------------------------------------------------------
+#ifndef PB_CHUNK_FLOATS
+#define PB_CHUNK_FLOATS 1024  // 4 KiB per bulk copy
+#endif
+#ifndef PB_STAGES
+#define PB_STAGES 3
+#endif
+constexpr int kChunkFloats = PB_CHUNK_FLOATS;
+constexpr int kChunkBytes = kChunkFloats * 4;
+constexpr int kStages = PB_STAGES;
+
+__host__ __device__ constexpr size_t tma_ring_smem_bytes(int warps) {
+  return (size_t)warps * kStages * kChunkBytes + (size_t)warps * kStages * 8;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct MapCursor {
+  int m;              // claimed map index (>= total: none)
+  const float* base;  // its first element
+  int issued;         // chunks handed to the copy engine so far
+};
+
+// Streams the maps handed out by `claim` (warp-uniform: returns the next map index, >= total
+// when there is none) through this warp's ring and calls sink(m, base, argmax) for each.
+// `prefetch(m)` runs before a map is scanned (e.g. to load its affine early).
+//   warps_per_block: ring slots laid out in dynamic shared memory `smem_raw`.
+template <typename Claim, typename Prefetch, typename Sink>
+__device__ __forceinline__ void stream_maps_tma(unsigned char* smem_raw, int warps_per_block,
+                                                const HmViews& hv, int J, int HW, int total,
+                                                Claim claim, Prefetch prefetch, Sink sink) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * kStages * kChunkFloats;
+  uint64_t* bars =
+      reinterpret_cast<uint64_t*>(smem_raw + (size_t)warps_per_block * kStages * kChunkBytes) + warp * kStages;
+  const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars);
+  if (lane == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(bars_s + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int nchunk = (HW + kChunkFloats - 1) / kChunkFloats;
+  const int last_floats = HW - (nchunk - 1) * kChunkFloats;
+  unsigned q_issue = 0, q_cons = 0;  // chunk sequence numbers of this warp (stage = q % kStages)
+
+  auto set_map = [&](MapCursor& c, int m) {
+    c.m = m;
+    c.issued = 0;
+    c.base = nullptr;
+    if (m < total) {
+      const int row = m / J;
+      c.base = map_base(hv, row, m - row * J, J, HW);
+    }
+  };
+  // hand the next chunk of `c` to the copy engine (lane 0 issues; cursors are warp-uniform)
+  auto issue = [&](MapCursor& c) {
+    const int k = c.issued;
+    const uint32_t bytes = (k == nchunk - 1 ? last_floats : kChunkFloats) * 4;
+    const unsigned s = q_issue % kStages;
+    if (lane == 0) {
+      mbar_expect_tx(bars_s + 8 * s, bytes);
+      bulk_g2s(ring_s + s * kChunkBytes, c.base + (size_t)k * kChunkFloats, bytes, bars_s + 8 * s);
+    }
+    ++c.issued;
+    ++q_issue;
+  };
+
+  MapCursor cur, nxt;
+  set_map(cur, claim());
+  set_map(nxt, total);
+  bool nxt_claimed = false;
+  // keep the ring full: chunks of the current map first, then of the next claimed map
+  auto top_up = [&]() {
+    while (q_issue - q_cons < (unsigned)kStages) {
+      if (cur.m < total && cur.issued < nchunk) { issue(cur); continue; }
+      if (!nxt_claimed) {
+        set_map(nxt, claim());
+        nxt_claimed = true;
+      }
+      if (nxt.m < total && nxt.issued < nchunk) { issue(nxt); continue; }
+      break;
+    }
+  };
+
+  while (cur.m < total) {
+    prefetch(cur.m);
+    float best = -INFINITY;
+    int bidx = 4 * lane < HW ? 4 * lane : 0x7fffffff;
+    bool nanp = false;
+    for (int k = 0; k < nchunk; ++k) {
+      top_up();
+      const unsigned s = q_cons % kStages;
+      mbar_wait(bars_s + 8 * s, (q_cons / kStages) & 1u);
+      // The compare chain reads the stage directly.  (Copying the chunk to registers first and
+      // re-arming the stage before the compares was measured 35 % SLOWER on B200: with every
+      // stage of every warp in flight the memory system is past its knee, see profiles/.)
+      const float4* src = reinterpret_cast<const float4*>(ring + s * kChunkFloats);
+      const int nvec = (k == nchunk - 1 ? last_floats : kChunkFloats) >> 2;
+      const int e0 = k * kChunkFloats + 4 * lane;
+      constexpr int U = kChunkFloats / 128;
+#define PB_SCAN_F4(q, e)                                                        \
+  nanp |= (q.x != q.x) | (q.y != q.y) | (q.z != q.z) | (q.w != q.w);           \
+  if (q.x > best) { best = q.x; bidx = (e); }                                   \
+  if (q.y > best) { best = q.y; bidx = (e) + 1; }                               \
+  if (q.z > best) { best = q.z; bidx = (e) + 2; }                               \
+  if (q.w > best) { best = q.w; bidx = (e) + 3; }
+      if (nvec == kChunkFloats / 4) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float4 q = src[u * 32 + lane];
+          PB_SCAN_F4(q, e0 + 128 * u)
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (u * 32 + lane < nvec) {
+            const float4 q = src[u * 32 + lane];
+            PB_SCAN_F4(q, e0 + 128 * u)
+          }
+        }
+      }
+#undef PB_SCAN_F4
+      __syncwarp();  // every lane is done with stage s before it is refilled
+      ++q_cons;
+    }
+    top_up();  // the next map's first chunks fly while this one is finished
+    ArgMax am;
+    if (__any_sync(0xffffffffu, nanp)) {  // rare: exact numpy NaN rules, re-read from L2
+      scan_map_exact(cur.base, HW, lane, best, bidx);
+      am = warp_argmax<true>(best, bidx);
+    } else {
+      am = warp_argmax<false>(best, bidx);
+    }
+    sink(cur.m, cur.base, am);
+    if (!nxt_claimed) set_map(nxt, claim());
+    cur = nxt;
+    set_map(nxt, total);
+    nxt_claimed = false;
+  }
+}
+
 }  // namespace pb200
 #endif

@@ -34,10 +34,13 @@
 
 namespace pb200 {
 
-constexpr int kFusedWarps = 8;
-constexpr int kChunkFloats = 1024;                  // 4 KiB per bulk copy
-constexpr int kChunkBytes = kChunkFloats * 4;
-constexpr int kStages = 3;                          // 8 warps x 3 x 4 KiB = 96 KiB per block, 2 blocks per SM
+#ifndef PB_FUSED_WARPS
+#define PB_FUSED_WARPS 8  // x kStages x 4 KiB = 96 KiB of ring per block, 2 blocks per SM
+#endif
+#ifndef PB_FUSED_MIN_BLOCKS
+#define PB_FUSED_MIN_BLOCKS 2
+#endif
+constexpr int kFusedWarps = PB_FUSED_WARPS;
 
 struct FusedParams {
   HmViews hv;
@@ -156,148 +159,22 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 4) lift_fused_kernel(const F
   block_exit(p);
 }
 
-// ---- variant 1: TMA bulk-copy ring front end ---------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-struct MapCursor {
-  int m;              // claimed map index (>= total: none)
-  const float* base;  // its first element
-  int issued;         // chunks handed to the copy engine so far
-};
-
-__global__ void __launch_bounds__(kFusedWarps * 32, 2) lift_fused_tma_kernel(const FusedParams p) {
+// ---- variant 1: TMA bulk-copy ring front end (csrc/decode.cuh::stream_maps_tma) -------------
+__global__ void __launch_bounds__(kFusedWarps * 32, PB_FUSED_MIN_BLOCKS) lift_fused_tma_kernel(const FusedParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * kStages * kChunkFloats;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kFusedWarps * kStages * kChunkBytes) +
-                   warp * kStages;
-  const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars);
-  if (lane == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(bars_s + 8 * s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-
-  const int J = p.J, V = p.V, H = p.H, W = p.W, HW = H * W;
+  const int lane = threadIdx.x & 31;
+  const int J = p.J, V = p.V, H = p.H, W = p.W;
   const int total = p.B * V * J;
-  const int nchunk = (HW + kChunkFloats - 1) / kChunkFloats;
-  const int last_floats = HW - (nchunk - 1) * kChunkFloats;
-  unsigned q_issue = 0, q_cons = 0;  // chunk sequence numbers of this warp (stage = q % kStages)
-
-  auto set_map = [&](MapCursor& c, int m) {
-    c.m = m;
-    c.issued = 0;
-    c.base = nullptr;
-    if (m < total) {
-      const int row = m / J;
-      c.base = map_base(p.hv, row, m - row * J, J, HW);
-    }
-  };
-  // hand the next chunk of `c` to the copy engine (lane 0 issues; cursors are warp-uniform)
-  auto issue = [&](MapCursor& c) {
-    const int k = c.issued;
-    const uint32_t bytes = (k == nchunk - 1 ? last_floats : kChunkFloats) * 4;
-    const unsigned s = q_issue % kStages;
-    if (lane == 0) {
-      mbar_expect_tx(bars_s + 8 * s, bytes);
-      bulk_g2s(ring_s + s * kChunkBytes, c.base + (size_t)k * kChunkFloats, bytes, bars_s + 8 * s);
-    }
-    ++c.issued;
-    ++q_issue;
-  };
-
-  MapCursor cur, nxt;
-  set_map(cur, __shfl_sync(0xffffffffu, claim(p, lane), 0));
-  set_map(nxt, total);
-  bool nxt_claimed = false;
-  // keep the ring full: chunks of the current map first, then of the next claimed map
-  auto top_up = [&]() {
-    while (q_issue - q_cons < (unsigned)kStages) {
-      if (cur.m < total && cur.issued < nchunk) { issue(cur); continue; }
-      if (!nxt_claimed) {
-        set_map(nxt, __shfl_sync(0xffffffffu, claim(p, lane), 0));
-        nxt_claimed = true;
-      }
-      if (nxt.m < total && nxt.issued < nchunk) { issue(nxt); continue; }
-      break;
-    }
-  };
-
-  while (cur.m < total) {
-    const int m = cur.m, row = m / J;
-    const Affine6 aff = load_affine(p.affine + 6 * (size_t)row);
-    float best = -INFINITY;
-    int bidx = 4 * lane < HW ? 4 * lane : 0x7fffffff;
-    bool nanp = false;
-    for (int k = 0; k < nchunk; ++k) {
-      top_up();
-      const unsigned s = q_cons % kStages;
-      mbar_wait(bars_s + 8 * s, (q_cons / kStages) & 1u);
-      const float4* src = reinterpret_cast<const float4*>(ring + s * kChunkFloats);
-      const int nvec = (k == nchunk - 1 ? last_floats : kChunkFloats) >> 2;
-      const int e0 = k * kChunkFloats + 4 * lane;
-#pragma unroll
-      for (int u = 0; u < kChunkFloats / 128; ++u) {
-        const int vi = u * 32 + lane;
-        if (vi < nvec) {
-          const float4 q = src[vi];
-          const int e = e0 + 128 * u;
-          nanp |= (q.x != q.x) | (q.y != q.y) | (q.z != q.z) | (q.w != q.w);
-          if (q.x > best) { best = q.x; bidx = e; }
-          if (q.y > best) { best = q.y; bidx = e + 1; }
-          if (q.z > best) { best = q.z; bidx = e + 2; }
-          if (q.w > best) { best = q.w; bidx = e + 3; }
-        }
-      }
-      __syncwarp();  // every lane is done with stage s before it is refilled
-      ++q_cons;
-    }
-    top_up();  // the next map's first chunks fly while this one is finished
-    ArgMax am;
-    if (__any_sync(0xffffffffu, nanp)) {  // rare: exact numpy NaN rules, re-read from L2
-      scan_map_exact(cur.base, HW, lane, best, bidx);
-      am = warp_argmax<true>(best, bidx);
-    } else {
-      am = warp_argmax<false>(best, bidx);
-    }
-    const DecodeOut o = finish_map(am, cur.base, H, W, true, aff, p.post_process != 0);
-    const int f = row / V;
-    lift_if_last(p, publish(p, m, f, o, lane), f, lane);
-    if (!nxt_claimed) {
-      set_map(nxt, __shfl_sync(0xffffffffu, claim(p, lane), 0));
-    }
-    cur = nxt;
-    set_map(nxt, total);
-    nxt_claimed = false;
-  }
+  Affine6 aff;
+  stream_maps_tma(
+      smem_raw, kFusedWarps, p.hv, J, H * W, total,
+      [&]() { return __shfl_sync(0xffffffffu, claim(p, lane), 0); },
+      [&](int m) { aff = load_affine(p.affine + 6 * (size_t)(m / J)); },
+      [&](int m, const float* base, ArgMax am) {
+        const DecodeOut o = finish_map(am, base, H, W, true, aff, p.post_process != 0);
+        const int f = (m / J) / V;
+        lift_if_last(p, publish(p, m, f, o, lane), f, lane);
+      });
   block_exit(p);
 }
 
@@ -356,7 +233,7 @@ extern "C" int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, in
   const long long need = ((long long)B * V * J + kFusedWarps - 1) / kFusedWarps;
   const bool tma = g_lift_variant == 1 && p.vec_ok;  // bulk copies need 16-byte aligned maps
   if (tma) {
-    const size_t smem = (size_t)kFusedWarps * kStages * kChunkBytes + (size_t)kFusedWarps * kStages * 8;
+    const size_t smem = tma_ring_smem_bytes(kFusedWarps);
     static int blocks_per_sm_tma = 0;
     if (blocks_per_sm_tma == 0) {
       PB_CUDA(cudaFuncSetAttribute(lift_fused_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
