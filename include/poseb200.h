@@ -198,6 +198,9 @@ int pb200_set_tuning(int key, int value);
  *   pair_bits [E, nbins0, nbins0/32] uint32 : the level-0 `pairwise_constraint`
  *             (lib/multiviews/pictorial.py:240) as a bit matrix, bit (j%32) of word
  *             [e][i][j/32] set iff P_e[i,j] != 0 (nbins0 = first_nbins^3)
+ *   use_lut   : 1 if pb200_pairwise_lut_check found the matrix to depend on the index offset
+ *             (|dy|,|dx|,|dz|) only -- true for matrices generated on the regular grid; the
+ *             kernel then keeps row 0 of each edge in shared memory instead of reading rows
  *   workspace : bytes from pb200_rpsm_workspace_bytes
  *   out_pose  [B,J,3] float64 ; out_trace [B, depth+1, J] int32 chosen bin per level (or NULL)
  */
@@ -206,7 +209,7 @@ int pb200_rpsm(const float* hm, int B, int V, int J, int H, int W,
                const double* campack, const int32_t* cam_index, const double* box_affine,
                int img_w, int img_h, const double* root, const double* limb,
                const int32_t* edges, const int32_t* order, int root_idx,
-               const uint32_t* pair_bits,
+               const uint32_t* pair_bits, int use_lut,
                int first_nbins, int recur_nbins, int recur_depth, double grid_size, double tolerance,
                void* workspace, size_t workspace_bytes,
                double* out_pose, int32_t* out_trace, void* stream);
@@ -218,6 +221,10 @@ int pb200_rpsm(const float* hm, int B, int V, int J, int H, int W,
  */
 int pb200_pairwise_level0(const double* avg_limb, int E, int nbins, double box_size,
                           uint32_t* pair_bits, void* stream);
+/* *out_flag |= 1 (device int32, zeroed by the caller) unless every P_e[i,j] equals
+ * P_e[0, (|dy|*n+|dx|)*n+|dz|], i.e. unless the bit matrix is a function of the offset only. */
+int pb200_pairwise_lut_check(const uint32_t* pair_bits, int E, int nbins, int32_t* out_flag,
+                             void* stream);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,21 @@ class PairwiseTable(object):
     def __init__(self, bits, nbins):
         self.bits = bits
         self.nbins = nbins
+        self._offset_only = None
+
+    @property
+    def offset_only(self):
+        """True if P[i,j] depends on the index offset (|dy|,|dx|,|dz|) only (checked once, on the GPU)."""
+        if self._offset_only is None:
+            n = int(round(self.nbins ** (1.0 / 3)))
+            if n ** 3 != self.nbins:
+                self._offset_only = False
+            else:
+                flag = rt.zeros((1,), torch.int32)
+                _lib.call('pb200_pairwise_lut_check', rt.ptr(self.bits), int(self.bits.shape[0]), n,
+                          rt.ptr(flag), rt.stream_ptr())
+                self._offset_only = int(flag.item()) == 0
+        return self._offset_only
 
     @classmethod
     def from_dict(cls, pairwise, body):
@@ -75,7 +90,7 @@ class PairwiseTable(object):
 
 
 def rpsm_batch(cams, heatmaps, boxes_center, boxes_scale, grid_centers, limb_lengths, pairwise,
-               config, body=None, return_trace=False):
+               config, body=None, return_trace=False, use_lut=True):
     """RPSM for B frames.
 
     cams         : CameraTable or list of B*V camera dicts (view-minor rows)
@@ -84,6 +99,7 @@ def rpsm_batch(cams, heatmaps, boxes_center, boxes_scale, grid_centers, limb_len
     grid_centers : [B, 3] float64 root locations
     limb_lengths : [B, E] float64 in ``body.edges()`` order
     pairwise     : PairwiseTable or the reference's dict
+    use_lut      : allow the shared-memory offset table when the pairwise matrix permits it
     Returns poses [B, J, 3] float64 (CUDA tensor if heatmaps is one), optionally the chosen
     bins per level [B, depth+1, J] int32.
     """
@@ -124,7 +140,7 @@ def rpsm_batch(cams, heatmaps, boxes_center, boxes_scale, grid_centers, limb_len
     trace = rt.empty((B, depth + 1, J), torch.int32) if return_trace else None
     _lib.call('pb200_rpsm', rt.ptr(hm), B, V, J, H, W, rt.ptr(table.pack), rt.ptr(table.index),
               rt.ptr(aff), int(img[0]), int(img[1]), rt.ptr(root), rt.ptr(limb),
-              rt.ptr(d_edges), rt.ptr(d_order), root_idx, rt.ptr(pw.bits),
+              rt.ptr(d_edges), rt.ptr(d_order), root_idx, rt.ptr(pw.bits), int(pw.offset_only and use_lut),
               n0, int(ps.RECUR_NBINS), depth, float(ps.GRID_SIZE), float(ps.LIMB_LENGTH_TOLERANCE),
               rt.ptr(ws), int(ws.numel()), rt.ptr(pose), rt.ptr(trace), rt.stream_ptr())
     if not rt.is_device_tensor(heatmaps):

@@ -90,3 +90,60 @@ def test_rpsm_17_joints_vs_oracle_and_gt(pict):
             assert np.abs(poses[f] - ref).max() < 0.13
         else:
             assert np.array_equal(poses[f], ref)
+
+
+def test_rpsm_bit_rows_and_offset_table_agree(pict):
+    """The shared-memory offset table and the bit-matrix rows are two readers of the same
+    predicate; a matrix that is NOT a function of the offset must take the row path."""
+    import torch
+    from pose_unsupervised_b200.multiviews.body import HumanBody
+    r = golden('rpsm.npz')
+    body, obody = HumanBody(), OracleBody()
+    cfg = rpsm_config()
+    avg = {e: float(l) for e, l in zip(obody.edges(), r['avg_limb'])}
+    table = pict.PairwiseTable.from_limb_lengths(avg, body, 2000, 16)
+    assert table.offset_only
+    hm, cam, boxes, root, limb, edges = rpsm_golden_frame(r, 0)
+    args = (cam, hm[None], np.array([b['center'] for b in boxes]), np.array([b['scale'] for b in boxes]),
+            root[None], np.array([[limb[e] for e in edges]]), table, cfg, body)
+    p_lut, t_lut = pict.rpsm_batch(*args, return_trace=True, use_lut=True)
+    p_row, t_row = pict.rpsm_batch(*args, return_trace=True, use_lut=False)
+    assert np.array_equal(t_lut, t_row) and np.array_equal(p_lut, p_row)
+    assert np.array_equal(t_lut[0], r['f0_trace'])
+    # knock one bit out: no longer translation invariant -> detected -> row path, and the result
+    # equals the oracle run on the same modified matrix
+    bits = table.bits.clone()
+    bits[6, 1234, 40] ^= 0x10
+    broken = pict.PairwiseTable(bits, 4096)
+    assert not broken.offset_only
+    dense = {e: broken.to_dense(k) for k, e in enumerate(edges)}
+    ref, rtrace = opict.rpsm(cam, hm, boxes, root, limb, dense, cfg, obody, return_trace=True)
+    p_b, t_b = pict.rpsm_batch(*args[:6], broken, cfg, body, return_trace=True)
+    assert np.array_equal(t_b[0], rtrace) and np.array_equal(p_b[0], ref)
+
+
+def test_rpsm_zero_and_negative_energies(pict):
+    """Disallowed children enter the reference's product as 0: when every allowed energy is <= 0
+    the zero wins at the first disallowed index.  Negative / all-zero heatmaps exercise that."""
+    from pose_unsupervised_b200.multiviews.body import HumanBody
+    r = golden('rpsm.npz')
+    body, obody = HumanBody(), OracleBody()
+    cfg = rpsm_config(depth=3)
+    avg = {e: float(l) for e, l in zip(obody.edges(), r['avg_limb'])}
+    table = pict.PairwiseTable.from_limb_lengths(avg, body, 2000, 16)
+    opw = opict.level0_pairwise(2000, avg, 16, obody)
+    hm, cam, boxes, root, limb, edges = rpsm_golden_frame(r, 1)
+    variants = []
+    neg = hm.copy(); neg[:, [0, 5, 9]] = -neg[:, [0, 5, 9]] - 0.01          # three joints all negative
+    variants.append(neg)
+    zero = hm.copy(); zero[:, [10, 15]] = 0.0                                 # two joints all zero
+    variants.append(zero)
+    shifted = hm - 0.05                                                       # mixed signs everywhere
+    variants.append(shifted.astype(np.float32))
+    for h in variants:
+        ref, rtrace = opict.rpsm(cam, h, boxes, root, limb, opw, cfg, obody, return_trace=True)
+        got, trace = pict.rpsm_batch(cam, h[None], np.array([b['center'] for b in boxes]),
+                                     np.array([b['scale'] for b in boxes]), root[None],
+                                     np.array([[limb[e] for e in edges]]), table, cfg, body, return_trace=True)
+        assert np.array_equal(trace[0], rtrace)
+        assert np.array_equal(got[0], ref)
