@@ -34,10 +34,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-V, J, HW = 4, 17, 64
-# algorithmic bytes per frame of decode + triangulate + reproject
-BYTES_PER_FRAME = V * J * HW * HW * 4 + V * J * 12 + V * 16 + V * 8 + J * 24 + V * J * 4   # 1,115,704
-METRIC = 'multiview frames/s (4 views x 17 joints, 64x64)'
+V, J, HW = 4, 17, 64                      # BASELINE.json configs[1]; --views/--joints/--hw run the sweep of configs[4]
+
+
+def bytes_per_frame():
+    """algorithmic bytes per frame of decode + triangulate + reproject
+    (heatmaps read once + xy/maxval + center/scale + camera ids + X + reprojection error)."""
+    return V * J * HW * HW * 4 + V * J * 12 + V * 16 + V * 8 + J * 24 + V * J * 4    # 1,115,704 at 4/17/64
+
+
+def metric_name():
+    return 'multiview frames/s (%d views x %d joints, %dx%d)' % (V, J, HW, HW)
 
 
 def measured_hbm_peak():
@@ -139,7 +146,7 @@ def _cpu_frames(args):
     t0 = time.perf_counter()
     preds, maxvals = oinf.get_final_preds_loops(True, hm, center, scale)        # lib/core/inference.py:50-75
     vis = np.ones(preds.shape[:2])
-    proj, _ = otri.reproject_poses(preds, cams, vis)                             # lib/multiviews/triangulate.py:169-213
+    proj, _ = otri.reproject_poses(preds, cams, vis, nviews=V)                             # lib/multiviews/triangulate.py:169-213
     _ = np.linalg.norm(proj - preds, axis=2)
     return time.perf_counter() - t0
 
@@ -188,7 +195,7 @@ def run_reference_arm(args):
     sample = '%d steps x %d frames (%d per process, %d processes) of the lift workload' % (
         steps, cores * per_worker, per_worker, cores)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus,
+        'impl': 'reference', 'metric': metric_name(), 'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': warmup, 'ms_per_step': 1e3 * dt / steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 decode, f64 lift', 'data': 'synthetic',
         'config': workload_config(cores * per_worker),
@@ -203,7 +210,7 @@ def workload_config(frames_per_gpu):
             'views': V, 'joints': J, 'heatmap': '%dx%d float32' % (HW, HW), 'frames_per_gpu': frames_per_gpu,
             'cameras': '28-camera table (7 rigs x 4 views)', 'post_process': True,
             'l2': 'no flush: each step streams %.2f GB per GPU, far above the 126 MB L2'
-                  % (frames_per_gpu * BYTES_PER_FRAME / 1e9)}
+                  % (frames_per_gpu * bytes_per_frame() / 1e9)}
 
 
 # ---------------------------------------------------------------------------------------
@@ -239,19 +246,23 @@ def run_ours(args):
     d_center, d_scale = rt.to_device(center), rt.to_device(scale)
     gt = torch.zeros((B, J, 3), dtype=torch.float64, device=dev)   # MPJPE reference for the exchange step
     nframes_total = B * world
+    # exchange step: ONE all-gather of [3D poses | MPJPE partial sums]; the lift kernel writes the
+    # poses straight into the send buffer
+    exch = parallel.PoseExchange(nframes_total, J, dev)
 
     def step(ev=None):
         aff = crop_affine(d_center, d_scale, (HW, HW), inv=1)
         if ev is not None:
             ev[0].record()
-        res = lift_heatmaps(hm, None, None, table, nviews=V, post_process=True, affine=aff)
+        res = lift_heatmaps(hm, None, None, table, nviews=V, post_process=True, affine=aff,
+                            out_poses3d=exch.poses_view())
         if ev is not None:
             ev[1].record()
-        stats = mpjpe_stats(res.poses3d, gt)
+        exch.stats_view().zero_()
+        mpjpe_stats(res.poses3d, gt, out=exch.stats_view())
         if world > 1:
-            parallel.gather_poses(res.poses3d, nframes_total)
-            stats = parallel.reduce_mpjpe(stats)
-        return res, stats
+            exch.run()
+        return res
 
     def fence():
         if world > 1:
@@ -261,23 +272,53 @@ def run_ours(args):
     for _ in range(warmup):
         step()
     fence()
+
+    # The whole step (3 kernels, a memset and the NCCL all-gather) is captured once in a CUDA graph
+    # and replayed: at ~0.8 ms per step the Python/launch overhead of the eager path is otherwise
+    # visible, above all at N > 1.
+    run_step, graphed = step, False
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            run_step, graphed = graph.replay, True
+            for _ in range(3):
+                run_step()
+        except Exception as e:   # fall back to eager launches, say so in the JSON line
+            sys.stderr.write('CUDA graph capture failed (%s); timing eager launches\n' % e)
+            run_step, graphed = step, False
+    fence()
+
     clocks = ClockSampler(local)
-    kernel_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                     for _ in range(steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks.start()
     fence()
     start.record()
     for i in range(steps):
-        step(kernel_events[i])
+        run_step()
     stop.record()
     fence()
     clock_info = clocks.stop()
     ms_total = parallel.max_over_ranks(start.elapsed_time(stop), dev)
+    value = nframes_total * steps / (ms_total * 1e-3)
+    launches_per_step = 4            # crop_affine_kernel, lift_fused(_tma)_kernel, memset of the 4 sums, mpjpe_kernel
+
+    # ---- the dominant kernel alone: CUDA events around every launch (eager pass, same work) ----
+    ksteps = min(steps, 50)
+    kernel_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                     for _ in range(ksteps)]
+    fence()
+    for i in range(ksteps):
+        step(kernel_events[i])
+    fence()
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
     kern_ms = parallel.max_over_ranks(kern_ms, dev)
-    value = nframes_total * steps / (ms_total * 1e-3)
-    launches_per_step = 3            # crop_affine_kernel, lift_fused_kernel, mpjpe_kernel
 
     # ---- end to end through the public numpy API, host buffers ------------------------------
     e2e_steps = max(1, min(3, steps))
@@ -305,21 +346,21 @@ def run_ours(args):
     e2e_value = nframes_total * e2e_steps / e2e_s
 
     # ---- sanity: the timed path is the real path (spot check against the oracle on rank 0) -----
-    res, _ = step()
+    res = step()
     torch.cuda.synchronize()
 
     line = None
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
-        achieved = B * BYTES_PER_FRAME / (kern_ms * 1e-3) / 1e9
+        achieved = B * bytes_per_frame() / (kern_ms * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline_leg()
         line = {
-            'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': steps,
+            'metric': metric_name(), 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': steps,
             'warmup': warmup, 'ms_per_step': ms_total / steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 decode, f64 lift', 'data': 'synthetic',
-            'config': workload_config(B),
+            'config': dict(workload_config(B), cuda_graph=graphed),
             'clocks': clock_info,
             'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps,
@@ -328,7 +369,7 @@ def run_ours(args):
             'roofline': {'bound': 'hbm', 'kernel': 'lift_fused_kernel' if args.lift_variant == 0 else 'lift_fused_tma_kernel', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                          'peak_source': peak_src, 'kernel_ms': kern_ms,
-                         'algorithmic_bytes_per_launch': B * BYTES_PER_FRAME},
+                         'algorithmic_bytes_per_launch': B * bytes_per_frame()},
             'cpu_baseline': cpu,
         }
         traffic = os.path.join(ROOT, 'profiles', 'lift_fused_traffic.json')
@@ -420,21 +461,112 @@ def run_rpsm(args):
                       'ms_per_step': ms, 'frames_per_s': B / (ms * 1e-3), 'mpjpe_mm_vs_synthetic_gt': err}))
 
 
+def run_pseudo(args):
+    """BASELINE.json configs[3] variant (ii): the pseudo-label pass of run/test/test_pseudo_label.py
+    from 2D locations -- confidence threshold, RANSAC view selection, triangulate + reproject,
+    epipolar residuals -- on `--frames` frames in total, sharded by frame over the ranks."""
+    import torch
+    import torch.distributed as dist
+    from pose_unsupervised_b200 import parallel, runtime as rt
+    from pose_unsupervised_b200.core.loss import FundamentalTable, epipolar_residuals
+    from pose_unsupervised_b200.multiviews.cameras import CameraTable, pack_camera
+    from pose_unsupervised_b200.multiviews.triangulate import ransac, reproject_poses
+    from pose_unsupervised_b200.utils import synth
+    from oracle import epipolar as oepi          # only to build the exact F table (input data)
+    from tests.util import pseudo_config
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    total = args.frames if args.frames != 4096 else 1000000
+    lo, hi = parallel.frame_shard(total, rank, world)
+    B = hi - lo
+    rng = np.random.default_rng(100 + rank)
+    rigs = synth.camera_table(7, 4, seed=0)
+    pack = np.array([pack_camera(c) for rig in rigs for c in rig])
+    subj = rng.integers(0, 7, B)
+    base = synth.random_poses(1024, seed=5)
+    poses = base[rng.integers(0, 1024, B)] + rng.normal(0, 15, (B, 17, 3))
+    obs = np.empty((B * 4, 17, 2))
+    for s_ in range(7):
+        sel = np.where(subj == s_)[0]
+        for v in range(4):
+            obs[sel * 4 + v] = synth.project_plumb_bob_numpy(poses[sel].reshape(-1, 3), rigs[s_][v]).reshape(len(sel), 17, 2)
+    obs += rng.normal(0, 2.0, obs.shape)
+    bad = rng.random(obs.shape[:2]) < 0.10
+    obs[bad] += rng.normal(0, 50.0, (int(bad.sum()), 2))
+    conf = rng.uniform(0.04, 1.12, obs.shape[:2]).astype(np.float32)
+    table = CameraTable.from_arrays(pack, (subj[:, None] * 4 + np.arange(4)[None]).reshape(-1))
+    ftab = FundamentalTable(oepi.fundamental_table({s_: rigs[s_] for s_ in range(7)}), 4)
+    d_obs = rt.to_device(obs.astype(np.float32))
+    d_conf = rt.to_device(conf)
+    d_subj = torch.from_numpy(subj).to(dev)
+    cfg = pseudo_config(10.0, 3, False)
+    subj_list = subj
+
+    def step():
+        vis = d_conf > 0.7                                            # test_pseudo_label.py:194
+        vis = ransac(d_obs, table, vis, cfg)                          # :221
+        proj, pvis, pts = reproject_poses(d_obs, table, vis, False, return_points=True)   # :237
+        resid = epipolar_residuals(proj, subj_list, ftab)             # test_fund_mtx.py:56-69 on the labels
+        if world > 1:
+            parallel.gather_poses(pts, total)
+        return proj, pvis, pts, resid
+
+    for _ in range(2):
+        out = step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = args.steps if args.steps else 5
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        out = step()
+    b.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = parallel.max_over_ranks(a.elapsed_time(b) / steps, dev)
+    if rank == 0:
+        proj, pvis, pts, resid = out
+        keep = float(pvis.float().mean())
+        err = float((pts.cpu().numpy() - poses)[pvis.view(B, 4, 17)[:, 0].cpu().numpy() > 0].__abs__().mean()) if B else 0.0
+        per_frame = 4 * 17 * 12 + 32 + 4 * 17 * 8 + 4 * 17 + 17 * 24 + 12 * 17 * 8
+        print(json.dumps({'workload': 'configs[3](ii): pseudo-label pass from 2D locations (conf>0.7, RANSAC 3 inliers/10 px, '
+                                      'reproject, epipolar residuals)', 'frames': total, 'n_gpus': world, 'ms_per_step': ms,
+                          'frames_per_s': total / (ms * 1e-3), 'algorithmic_GBps': total * per_frame / (ms * 1e-3) / 1e9,
+                          'labels_kept': keep, 'mean_abs_3d_err_mm': err}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=0)
     ap.add_argument('--warmup', type=int, default=None)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='lift', choices=['lift', 'rpsm'])
+    ap.add_argument('--workload', default='lift', choices=['lift', 'rpsm', 'pseudo'])
+    ap.add_argument('--views', type=int, default=4)
+    ap.add_argument('--joints', type=int, default=17)
+    ap.add_argument('--hw', type=int, default=64, help='heatmap side')
     ap.add_argument('--frames', type=int, default=4096, help='frames per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA graph replay')
     ap.add_argument('--lift-variant', type=int, default=None, help='0 = LDG front end, 1 = TMA ring (default)')
     args = ap.parse_args()
+    global V, J, HW
+    V, J, HW = args.views, args.joints, args.hw
     if args.impl == 'reference':
         run_reference_arm(args)
     elif args.workload == 'rpsm':
         run_rpsm(args)
+    elif args.workload == 'pseudo':
+        run_pseudo(args)
     else:
         run_ours(args)
 

@@ -326,35 +326,27 @@ __device__ __forceinline__ void stream_maps_tma(unsigned char* smem_raw, int war
       top_up();
       const unsigned s = q_cons % kStages;
       mbar_wait(bars_s + 8 * s, (q_cons / kStages) & 1u);
-      // The compare chain reads the stage directly.  (Copying the chunk to registers first and
-      // re-arming the stage before the compares was measured 35 % SLOWER on B200: with every
-      // stage of every warp in flight the memory system is past its knee, see profiles/.)
+      // The compare chain reads the stage directly, one float4 at a time.  Two "obvious"
+      // improvements were measured on B200 and rejected (profiles/r01_sweep_ring.txt): copying
+      // the chunk to registers and re-arming the stage before the compares (+37 % time), and
+      // an unguarded fast path for full chunks, which lets ptxas hoist all eight LDS.128 ahead
+      // of the compares (+35 % time at 64x64).
       const float4* src = reinterpret_cast<const float4*>(ring + s * kChunkFloats);
       const int nvec = (k == nchunk - 1 ? last_floats : kChunkFloats) >> 2;
       const int e0 = k * kChunkFloats + 4 * lane;
-      constexpr int U = kChunkFloats / 128;
-#define PB_SCAN_F4(q, e)                                                        \
-  nanp |= (q.x != q.x) | (q.y != q.y) | (q.z != q.z) | (q.w != q.w);           \
-  if (q.x > best) { best = q.x; bidx = (e); }                                   \
-  if (q.y > best) { best = q.y; bidx = (e) + 1; }                               \
-  if (q.z > best) { best = q.z; bidx = (e) + 2; }                               \
-  if (q.w > best) { best = q.w; bidx = (e) + 3; }
-      if (nvec == kChunkFloats / 4) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float4 q = src[u * 32 + lane];
-          PB_SCAN_F4(q, e0 + 128 * u)
-        }
-      } else {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (u * 32 + lane < nvec) {
-            const float4 q = src[u * 32 + lane];
-            PB_SCAN_F4(q, e0 + 128 * u)
-          }
+      for (int u = 0; u < kChunkFloats / 128; ++u) {
+        const int vi = u * 32 + lane;
+        if (vi < nvec) {
+          const float4 q = src[vi];
+          const int e = e0 + 128 * u;
+          nanp |= (q.x != q.x) | (q.y != q.y) | (q.z != q.z) | (q.w != q.w);
+          if (q.x > best) { best = q.x; bidx = e; }
+          if (q.y > best) { best = q.y; bidx = e + 1; }
+          if (q.z > best) { best = q.z; bidx = e + 2; }
+          if (q.w > best) { best = q.w; bidx = e + 3; }
         }
       }
-#undef PB_SCAN_F4
       __syncwarp();  // every lane is done with stage s before it is refilled
       ++q_cons;
     }

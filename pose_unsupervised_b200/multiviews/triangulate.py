@@ -94,7 +94,7 @@ class LiftResult(object):
 
 def lift_heatmaps(heatmaps, center, scale, camera_params, nviews=4, post_process=True,
                   no_distortion=False, conf_thre=None, return_idx=False, return_proj=False,
-                  affine=None):
+                  affine=None, out_poses3d=None):
     """Heatmaps -> 2D joints -> 3D poses -> reprojection error in one pass over HBM.
 
     Equivalent to ``get_final_preds`` (lib/core/inference.py:50-75) on every row followed by
@@ -102,7 +102,9 @@ def lift_heatmaps(heatmaps, center, scale, camera_params, nviews=4, post_process
     ``joints_vis = maxvals > conf_thre`` (run/test/test_pseudo_label.py:194; all visible when
     ``conf_thre`` is None).  heatmaps: [B*V,J,H,W] float32 view-minor, or a list of V
     per-view tensors [B,J,H,W].  ``affine`` may carry the [N,2,3] result of
-    ``crop_affine(center, scale, (W, H), inv=1)`` when the caller already has it.
+    ``crop_affine(center, scale, (W, H), inv=1)`` when the caller already has it;
+    ``out_poses3d`` a preallocated CUDA float64 [B,J,3] tensor to write the poses into (e.g. the
+    send buffer of ``parallel.PoseExchange``).
     """
     rt.require_device()
     views, N, J, H, W = _view_pointers(heatmaps)
@@ -121,7 +123,13 @@ def lift_heatmaps(heatmaps, center, scale, camera_params, nviews=4, post_process
     xy = rt.empty((N, J, 2), torch.float32)
     maxvals = rt.empty((N, J), torch.float32)
     idx = rt.empty((N, J), torch.int32) if return_idx else None
-    poses3d = rt.empty((B, J, 3), torch.float64)
+    if out_poses3d is None:
+        poses3d = rt.empty((B, J, 3), torch.float64)
+    else:
+        poses3d = out_poses3d
+        if poses3d.dtype != torch.float64 or tuple(poses3d.shape) != (B, J, 3) or \
+                not poses3d.is_cuda or not poses3d.is_contiguous():
+            raise ValueError('out_poses3d must be a contiguous CUDA float64 [%d, %d, 3] tensor' % (B, J))
     err = rt.empty((N, J), torch.float32)
     proj = rt.empty((N, J, 2), torch.float64) if return_proj else None
     ws = rt.workspace('lift', _lib.load().pb200_lift_workspace_bytes(B, nviews, J))

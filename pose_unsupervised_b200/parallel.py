@@ -61,6 +61,49 @@ def reduce_mpjpe(stats, group=None):
     return torch.stack([sums[0], sums[1], mx[0], sums[2]])
 
 
+class PoseExchange(object):
+    """The exchange step as ONE collective: every rank contributes [its poses | its 4 MPJPE sums].
+
+    The send buffer is where the lift kernel writes its 3D poses (``poses_view``) and where
+    ``mpjpe_stats`` accumulates (``stats_view``), so nothing is copied before the all-gather;
+    buffers are allocated once, which also makes the whole step capturable in a CUDA graph.
+    Shards may be uneven (the last rank takes the remainder): every rank sends ``cap`` frames.
+    """
+
+    def __init__(self, nframes, njoints, device, group=None, dtype=torch.float64):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.nframes, self.njoints = nframes, njoints
+        self.counts = [hi - lo for lo, hi in (frame_shard(nframes, r, self.world) for r in range(self.world))]
+        self.cap = max(self.counts)
+        self.width = self.cap * njoints * 3 + 4
+        self.send = torch.zeros(self.width, dtype=dtype, device=device)
+        self.recv = torch.zeros(self.world * self.width, dtype=dtype, device=device)
+
+    def poses_view(self):
+        b = self.counts[self.rank]
+        return self.send[:b * self.njoints * 3].view(b, self.njoints, 3)
+
+    def stats_view(self):
+        return self.send[self.width - 4:]
+
+    def run(self):
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        else:
+            self.recv.copy_(self.send)
+
+    def gathered_poses(self):
+        rows = self.recv.view(self.world, self.width)
+        return torch.cat([rows[r, :self.counts[r] * self.njoints * 3].view(self.counts[r], self.njoints, 3)
+                          for r in range(self.world)], dim=0)
+
+    def reduced_stats(self):
+        st = self.recv.view(self.world, self.width)[:, self.width - 4:]
+        return torch.stack([st[:, 0].sum(), st[:, 1].sum(), st[:, 2].max(), st[:, 3].sum()])
+
+
 def max_over_ranks(value, device, group=None):
     """Scalar max over ranks (timing: a step takes as long as its slowest rank)."""
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)

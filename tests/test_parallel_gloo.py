@@ -34,6 +34,13 @@ def _worker(rank, world, port, nframes, q):
                              torch.tensor(float(err.numel()), dtype=torch.float64)])
         red = parallel.reduce_mpjpe(stats)
         t = parallel.max_over_ranks(1.0 + rank, torch.device('cpu'))
+        # the one-collective form used by bench.py
+        ex = parallel.PoseExchange(nframes, 17, torch.device('cpu'))
+        ex.poses_view().copy_(pred[lo:hi])
+        ex.stats_view().copy_(stats)
+        ex.run()
+        red2 = ex.reduced_stats()
+        assert torch.equal(ex.gathered_poses(), pred) and torch.allclose(red2, red)
         all_err = (pred - gt).norm(dim=2)
         ok = torch.equal(full, pred) and abs(float(red[0]) - float(all_err.sum())) < 1e-6 \
             and float(red[2]) == float(all_err.max()) and float(red[3]) == all_err.numel() \
