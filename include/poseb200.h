@@ -177,8 +177,10 @@ int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, int B, int V,
                      double* out_X, float* out_err, double* out_proj,
                      void* workspace, void* stream);
 
-/* Tuning hook (process-wide).  PB200_TUNE_LIFT_VARIANT: streaming front end of
- * pb200_lift_fused, 0 = LDG.128, 1 = per-warp TMA bulk-copy ring (default). */
+/* Tuning hook (process-wide).  PB200_TUNE_LIFT_VARIANT selects how pb200_lift_fused runs:
+ * 0 = one fused kernel, LDG.128 front end; 1 = one fused kernel, per-warp TMA bulk-copy ring;
+ * 2 = two kernels back to back (TMA decode, then one thread per (frame, joint)) -- the default,
+ * fastest on B200.  All three give identical results. */
 #define PB200_TUNE_LIFT_VARIANT 1
 int pb200_set_tuning(int key, int value);
 

@@ -32,20 +32,21 @@ def _view_pointers(heatmaps):
     return views, n * len(views), j, h, w
 
 
-def decode_heatmaps(heatmaps, center=None, scale=None, post_process=False, return_idx=False):
+def decode_heatmaps(heatmaps, center=None, scale=None, post_process=False, return_idx=False, affine=None):
     """Decode on the device.
 
     heatmaps : [N,J,H,W] float32 (numpy or CUDA tensor), or a list of V per-view
                tensors [N/V,J,H,W] (rows of the result are then frame*V + view).
     center, scale : [N,2]; when given the result is in image pixels
                (get_final_preds), otherwise masked heatmap pixels (get_max_preds).
+    affine   : optionally the precomputed ``crop_affine(center, scale, (W, H), inv=1)`` [N,2,3].
     Returns CUDA tensors (xy [N,J,2] float32, maxvals [N,J] float32[, idx [N,J] int32]).
     """
     rt.require_device()
     views, N, J, H, W = _view_pointers(heatmaps)
-    affine = None
-    if center is not None:
+    if affine is None and center is not None:
         affine = crop_affine(center, scale, (W, H), inv=1)
+    if affine is not None:
         if affine.shape[0] != N:
             raise ValueError('center/scale have %d rows, heatmaps %d' % (affine.shape[0], N))
     xy = rt.empty((N, J, 2), torch.float32)

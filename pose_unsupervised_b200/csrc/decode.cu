@@ -36,7 +36,10 @@ decode_kernel(HmViews hv, int N, int J, int H, int W, int vec_ok,
 
 // Same decode with the TMA ring front end (decode.cuh::stream_maps_tma); warps take maps
 // blockIdx*8+warp, +gridDim*8, ... so no claim counter is needed.
-__global__ void __launch_bounds__(kDecodeWarps * 32, 2)
+#ifndef PB_DECODE_MIN_BLOCKS
+#define PB_DECODE_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(kDecodeWarps * 32, PB_DECODE_MIN_BLOCKS)
 decode_tma_kernel(HmViews hv, int N, int J, int H, int W, const double* __restrict__ affine,
                   int post_process, float* __restrict__ out_xy, float* __restrict__ out_maxval,
                   int32_t* __restrict__ out_idx) {
@@ -46,23 +49,22 @@ decode_tma_kernel(HmViews hv, int N, int J, int H, int W, const double* __restri
   const int total = (int)total_ll;
   const long long stride = (long long)gridDim.x * kDecodeWarps;
   long long next = (long long)blockIdx.x * kDecodeWarps + warp;
-  Affine6 aff;
   stream_maps_tma(
-      smem_raw, kDecodeWarps, hv, J, H * W, total,
+      smem_raw, kDecodeWarps, hv, J, H, W, total, affine, post_process != 0,
       [&]() {
         const long long m = next;
         next += stride;
         return m < total_ll ? (int)m : total;
       },
-      [&](int m) { if (affine) aff = load_affine(affine + 6 * (size_t)(m / J)); },
-      [&](int m, const float* base, ArgMax am) {
-        const DecodeOut o = finish_map(am, base, H, W, affine != nullptr, aff, post_process != 0);
+      [&](int m, const DecodeOut& o) {
         if (lane == 0) {
           reinterpret_cast<float2*>(out_xy)[m] = make_float2(o.x, o.y);
           out_maxval[m] = o.maxval;
           if (out_idx) out_idx[m] = o.idx;
         }
-      });
+        return 0;
+      },
+      [&](int, int) {});
 }
 
 __global__ void crop_affine_kernel(const void* center, int c_f64, const void* scale, int s_f64, int n,
@@ -109,6 +111,11 @@ extern "C" int pb200_crop_affine(const void* center, int center_dtype, const voi
   return PB200_OK;
 }
 
+namespace pb200 {
+int launch_decode(const HmViews& hv, int N, int J, int H, int W, const double* affine, int post_process,
+                  float* out_xy, float* out_maxval, int32_t* out_idx, void* stream);
+}
+
 extern "C" int pb200_decode(const float* const* hm_views_host, int n_ptr, int N, int J, int H, int W,
                             const double* affine, int post_process, float* out_xy, float* out_maxval,
                             int32_t* out_idx, void* stream) {
@@ -119,6 +126,12 @@ extern "C" int pb200_decode(const float* const* hm_views_host, int n_ptr, int N,
   HmViews hv;
   int rc = fill_views(hm_views_host, n_ptr, N, hv);
   if (rc != PB200_OK) return rc;
+  return launch_decode(hv, N, J, H, W, affine, post_process, out_xy, out_maxval, out_idx, stream);
+}
+
+int pb200::launch_decode(const HmViews& hv, int N, int J, int H, int W, const double* affine,
+                         int post_process, float* out_xy, float* out_maxval, int32_t* out_idx,
+                         void* stream) {
   const long long maps = (long long)N * J;
   const int sm = cached_sm_count();
   if (sm <= 0) return PB200_ERR_CUDA;

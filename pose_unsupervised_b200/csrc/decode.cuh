@@ -187,6 +187,69 @@ __device__ __forceinline__ DecodeOut finish_map(const ArgMax am, const float* __
   return o;
 }
 
+// The same epilogue split in two so that the TMA front end can overlap it with the next map:
+// begin_finish issues the four neighbour loads of the quarter-pixel shift (L2 hits) and
+// returns without waiting for them; end_finish consumes them.
+struct PendingMap {
+  int m;  // map index, -1 = none
+  const float* base;
+  ArgMax am;
+  float fx, fy;          // masked heatmap coordinates
+  float xp, xm, yp, ym;  // hm[py][px+1], hm[py][px-1], hm[py+1][px], hm[py-1][px]
+  bool refine;
+  Affine6 aff;
+  int ticket;            // whatever the caller's publish step returned (e.g. an atomic's result)
+};
+
+__device__ __forceinline__ void begin_finish(PendingMap& pd, int m, const float* __restrict__ base,
+                                             const ArgMax am, int H, int W, bool has_trans,
+                                             bool post_process, const Affine6& aff) {
+  pd.m = m;
+  pd.base = base;
+  pd.am = am;
+  pd.aff = aff;
+  float fx = (float)(am.idx % W);
+  float fy = (float)(am.idx / W);
+  if (!(am.val > 0.0f)) { fx = 0.0f; fy = 0.0f; }  // pred_mask (inference.py:43-46)
+  pd.fx = fx;
+  pd.fy = fy;
+  pd.refine = false;
+  pd.xp = pd.xm = pd.yp = pd.ym = 0.0f;
+  if (has_trans && post_process) {
+    const int px = (int)floorf(fx + 0.5f), py = (int)floorf(fy + 0.5f);
+    if (1 < px && px < W - 1 && 1 < py && py < H - 1) {
+      const float* c = base + py * W + px;
+      pd.refine = true;
+      pd.xp = __ldg(c + 1); pd.xm = __ldg(c - 1);
+      pd.yp = __ldg(c + W); pd.ym = __ldg(c - W);
+    }
+  }
+}
+
+__device__ __forceinline__ DecodeOut end_finish(const PendingMap& pd, bool has_trans) {
+  DecodeOut o;
+  o.idx = pd.am.idx;
+  o.maxval = pd.am.val;
+  float fx = pd.fx, fy = pd.fy;
+  if (has_trans) {
+    if (pd.refine) {
+      const float dx = pd.xp - pd.xm, dy = pd.yp - pd.ym;
+      const float sx = dx > 0.f ? 1.f : (dx < 0.f ? -1.f : (dx == 0.f ? 0.f : dx));
+      const float sy = dy > 0.f ? 1.f : (dy < 0.f ? -1.f : (dy == 0.f ? 0.f : dy));
+      fx += sx * 0.25f;
+      fy += sy * 0.25f;
+    }
+    const double dxx = (double)fx, dyy = (double)fy;
+    const double ox = fma(dyy, pd.aff.t[1], dxx * pd.aff.t[0]) + pd.aff.t[2];
+    const double oy = fma(dyy, pd.aff.t[4], dxx * pd.aff.t[3]) + pd.aff.t[5];
+    fx = (float)ox;
+    fy = (float)oy;
+  }
+  o.x = fx;
+  o.y = fy;
+  return o;
+}
+
 // Whole-warp decode of one map; every lane returns the same result.
 __device__ __forceinline__ DecodeOut decode_map(const float* __restrict__ base, int H, int W, bool vec_ok,
                                                 const double* __restrict__ trans /* 6 or null */,
@@ -209,7 +272,14 @@ __device__ __forceinline__ DecodeOut decode_map(const float* __restrict__ base, 
 #define PB_CHUNK_FLOATS 1024  // 4 KiB per bulk copy
 #endif
 #ifndef PB_STAGES
-#define PB_STAGES 3
+#define PB_STAGES 2
+#endif
+#ifndef PB_PIPE_EPILOGUE
+#define PB_PIPE_EPILOGUE 0  // 0: epilogue in line; 1: overlapped with the next map's chunks;
+                            // 2: in line, but complete(m, ticket) runs one map late
+#endif
+#ifndef PB_SCAN_HOIST
+#define PB_SCAN_HOIST 0     // 1: unguarded fast path for full chunks (lets ptxas batch the LDS)
 #endif
 constexpr int kChunkFloats = PB_CHUNK_FLOATS;
 constexpr int kChunkBytes = kChunkFloats * 4;
@@ -256,13 +326,19 @@ struct MapCursor {
 };
 
 // Streams the maps handed out by `claim` (warp-uniform: returns the next map index, >= total
-// when there is none) through this warp's ring and calls sink(m, base, argmax) for each.
-// `prefetch(m)` runs before a map is scanned (e.g. to load its affine early).
-//   warps_per_block: ring slots laid out in dynamic shared memory `smem_raw`.
-template <typename Claim, typename Prefetch, typename Sink>
+// when there is none) through this warp's ring and decodes them.  The per-map epilogue is
+// software-pipelined against the NEXT map's chunks:
+//   after the warp reduction   begin_finish: neighbour loads issued, not awaited
+//   after the next chunk 0     end_finish + publish(m, out) -> ticket   (stores / atomic issued)
+//   after the next chunk 1     complete(m, ticket)                      (ticket consumed, e.g. lift)
+// so the L2 and atomic round trips never stall the stream.
+//   affine: [rows][6] or null (get_max_preds); warps_per_block: ring slots in `smem_raw`.
+template <typename Claim, typename Publish, typename Complete>
 __device__ __forceinline__ void stream_maps_tma(unsigned char* smem_raw, int warps_per_block,
-                                                const HmViews& hv, int J, int HW, int total,
-                                                Claim claim, Prefetch prefetch, Sink sink) {
+                                                const HmViews& hv, int J, int H, int W, int total,
+                                                const double* __restrict__ affine, bool post_process,
+                                                Claim claim, Publish publish, Complete complete) {
+  const int HW = H * W;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * kStages * kChunkFloats;
   uint64_t* bars =
@@ -317,8 +393,14 @@ __device__ __forceinline__ void stream_maps_tma(unsigned char* smem_raw, int war
     }
   };
 
+  PendingMap pend;
+  pend.m = -1;
+  int late_m = -1, late_ticket = 0;
+  const bool has_trans = affine != nullptr;
+  const int k_complete = nchunk > 1 ? 1 : 0;
   while (cur.m < total) {
-    prefetch(cur.m);
+    Affine6 aff;
+    if (has_trans) aff = load_affine(affine + 6 * (size_t)(cur.m / J));  // consumed two stages later
     float best = -INFINITY;
     int bidx = 4 * lane < HW ? 4 * lane : 0x7fffffff;
     bool nanp = false;
@@ -334,21 +416,35 @@ __device__ __forceinline__ void stream_maps_tma(unsigned char* smem_raw, int war
       const float4* src = reinterpret_cast<const float4*>(ring + s * kChunkFloats);
       const int nvec = (k == nchunk - 1 ? last_floats : kChunkFloats) >> 2;
       const int e0 = k * kChunkFloats + 4 * lane;
+#define PB_SCAN_F4(q, e)                                                        \
+  nanp |= (q.x != q.x) | (q.y != q.y) | (q.z != q.z) | (q.w != q.w);           \
+  if (q.x > best) { best = q.x; bidx = (e); }                                   \
+  if (q.y > best) { best = q.y; bidx = (e) + 1; }                               \
+  if (q.z > best) { best = q.z; bidx = (e) + 2; }                               \
+  if (q.w > best) { best = q.w; bidx = (e) + 3; }
+      if (PB_SCAN_HOIST && nvec == kChunkFloats / 4) {
 #pragma unroll
-      for (int u = 0; u < kChunkFloats / 128; ++u) {
-        const int vi = u * 32 + lane;
-        if (vi < nvec) {
-          const float4 q = src[vi];
-          const int e = e0 + 128 * u;
-          nanp |= (q.x != q.x) | (q.y != q.y) | (q.z != q.z) | (q.w != q.w);
-          if (q.x > best) { best = q.x; bidx = e; }
-          if (q.y > best) { best = q.y; bidx = e + 1; }
-          if (q.z > best) { best = q.z; bidx = e + 2; }
-          if (q.w > best) { best = q.w; bidx = e + 3; }
+        for (int u = 0; u < kChunkFloats / 128; ++u) {
+          const float4 q = src[u * 32 + lane];
+          PB_SCAN_F4(q, e0 + 128 * u)
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < kChunkFloats / 128; ++u) {
+          const int vi = u * 32 + lane;
+          if (vi < nvec) {
+            const float4 q = src[vi];
+            PB_SCAN_F4(q, e0 + 128 * u)
+          }
         }
       }
+#undef PB_SCAN_F4
       __syncwarp();  // every lane is done with stage s before it is refilled
       ++q_cons;
+      if (PB_PIPE_EPILOGUE == 1 && pend.m >= 0) {  // previous map's epilogue, interleaved with this map's chunks
+        if (k == 0) pend.ticket = publish(pend.m, end_finish(pend, has_trans));
+        if (k == k_complete) { complete(pend.m, pend.ticket); pend.m = -1; }
+      }
     }
     top_up();  // the next map's first chunks fly while this one is finished
     ArgMax am;
@@ -358,12 +454,30 @@ __device__ __forceinline__ void stream_maps_tma(unsigned char* smem_raw, int war
     } else {
       am = warp_argmax<false>(best, bidx);
     }
-    sink(cur.m, cur.base, am);
+    begin_finish(pend, cur.m, cur.base, am, H, W, has_trans, post_process, aff);
+    if (PB_PIPE_EPILOGUE == 0) {
+      pend.ticket = publish(pend.m, end_finish(pend, has_trans));
+      complete(pend.m, pend.ticket);
+      pend.m = -1;
+    } else if (PB_PIPE_EPILOGUE == 2) {
+      // publish now (its stores and atomic are issued), consume the PREVIOUS map's ticket: by
+      // now that atomic has long returned, so no round trip is ever waited for
+      const int ticket = publish(pend.m, end_finish(pend, has_trans));
+      if (late_m >= 0) complete(late_m, late_ticket);
+      late_m = pend.m;
+      late_ticket = ticket;
+      pend.m = -1;
+    }
     if (!nxt_claimed) set_map(nxt, claim());
     cur = nxt;
     set_map(nxt, total);
     nxt_claimed = false;
   }
+  if (pend.m >= 0) {  // drain
+    pend.ticket = publish(pend.m, end_finish(pend, has_trans));
+    complete(pend.m, pend.ticket);
+  }
+  if (late_m >= 0) complete(late_m, late_ticket);
 }
 
 }  // namespace pb200

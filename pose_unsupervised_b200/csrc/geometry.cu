@@ -35,6 +35,11 @@ struct GeoParams {
   double* out_proj;
   uint8_t* out_vis;
   double* out_err;
+  // lift_after_decode only: visibility = maxval > conf_thre, float32 error output
+  const float* maxval;
+  int use_conf;
+  float conf_thre;
+  float* out_err32;
 };
 
 template <typename T, int kMode>
@@ -47,8 +52,11 @@ __global__ void __launch_bounds__(128) geometry_kernel(GeoParams p) {
   const int32_t* cam_row = p.cam_index + row0;
   XYLoader<T> xy{reinterpret_cast<const T*>(p.xy) + (row0 * J + j) * 2, J * 2};
   uint32_t mask = 0u;
-  for (int v = 0; v < V; ++v)
-    if (p.vis == nullptr || p.vis[(row0 + v) * J + j]) mask |= 1u << v;
+  for (int v = 0; v < V; ++v) {
+    bool on = p.vis == nullptr || p.vis[(row0 + v) * J + j];
+    if (p.use_conf) on = p.maxval[(row0 + v) * J + j] > p.conf_thre;
+    if (on) mask |= 1u << v;
+  }
   const bool nd = p.no_dist != 0;
 
   if (kMode == kModeRansac) {
@@ -68,10 +76,10 @@ __global__ void __launch_bounds__(128) geometry_kernel(GeoParams p) {
       double pu = 0.0, pv = 0.0, e = 0.0;
       if (nv >= 2) e = reproject_view(p.campack, cam_row, v, nd, X, xy, pu, pv);
       const size_t o = (row0 + v) * J + j;
-      p.out_proj[2 * o] = pu;
-      p.out_proj[2 * o + 1] = pv;
-      p.out_vis[o] = nv >= 2 ? 1 : 0;
+      if (p.out_proj) { p.out_proj[2 * o] = pu; p.out_proj[2 * o + 1] = pv; }
+      if (p.out_vis) p.out_vis[o] = nv >= 2 ? 1 : 0;
       if (p.out_err) p.out_err[o] = e;
+      if (p.out_err32) p.out_err32[o] = (float)e;
     }
   }
 }
@@ -189,6 +197,16 @@ static int launch_geo(const GeoParams& p, int xy_dtype, void* stream) {
   return PB200_OK;
 }
 
+// The lifting half of the two-kernel lift path (lift_fused.cu, variant 2): triangulate and
+// reproject the float32 coordinates the decode kernel just wrote.
+int launch_lift_after_decode(const double* campack, const int32_t* cam_index, const float* xy,
+                             const float* maxval, int use_conf, float conf_thre, int B, int V, int J,
+                             int no_dist, double* out_X, float* out_err32, double* out_proj, void* stream) {
+  GeoParams p{campack, cam_index, xy, nullptr, B, V, J, no_dist, 0.0, 0, out_X, out_proj, nullptr, nullptr,
+              maxval, use_conf, conf_thre, out_err32};
+  return launch_geo<kModeReproject>(p, PB200_F32, stream);
+}
+
 }  // namespace pb200
 
 using namespace pb200;
@@ -210,7 +228,8 @@ extern "C" int pb200_triangulate(const double* campack, const int32_t* cam_index
   int rc = check_geo(campack, cam_index, xy, xy_dtype, B, V, J);
   if (rc != PB200_OK) return rc;
   PB_REQUIRE(out_X, "out_X is null");
-  GeoParams p{campack, cam_index, xy, vis, B, V, J, no_distortion, 0.0, 0, out_X, nullptr, nullptr, nullptr};
+  GeoParams p{campack, cam_index, xy, vis, B, V, J, no_distortion, 0.0, 0, out_X, nullptr, nullptr, nullptr,
+              nullptr, 0, 0.f, nullptr};
   return launch_geo<kModeTriangulate>(p, xy_dtype, stream);
 }
 
@@ -221,7 +240,8 @@ extern "C" int pb200_reproject(const double* campack, const int32_t* cam_index, 
   int rc = check_geo(campack, cam_index, xy, xy_dtype, B, V, J);
   if (rc != PB200_OK) return rc;
   PB_REQUIRE(out_proj && out_vis, "out_proj / out_vis is null");
-  GeoParams p{campack, cam_index, xy, vis, B, V, J, no_distortion, 0.0, 0, out_X, out_proj, out_vis, out_err};
+  GeoParams p{campack, cam_index, xy, vis, B, V, J, no_distortion, 0.0, 0, out_X, out_proj, out_vis, out_err,
+              nullptr, 0, 0.f, nullptr};
   return launch_geo<kModeReproject>(p, xy_dtype, stream);
 }
 
@@ -233,7 +253,7 @@ extern "C" int pb200_ransac(const double* campack, const int32_t* cam_index, con
   PB_REQUIRE(out_vis, "out_vis is null");
   PB_REQUIRE(num_inliers >= 1, "num_inliers must be >= 1 (the reference divides by it)");
   GeoParams p{campack, cam_index, xy, vis, B, V, J, no_distortion, reproj_thre, num_inliers,
-              nullptr, nullptr, out_vis, nullptr};
+              nullptr, nullptr, out_vis, nullptr, nullptr, 0, 0.f, nullptr};
   return launch_geo<kModeRansac>(p, xy_dtype, stream);
 }
 

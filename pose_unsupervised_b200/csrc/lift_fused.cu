@@ -40,6 +40,12 @@ namespace pb200 {
 #ifndef PB_FUSED_MIN_BLOCKS
 #define PB_FUSED_MIN_BLOCKS 2
 #endif
+#ifndef PB_CLAIM_BATCH
+#define PB_CLAIM_BATCH 2   // maps taken per atomic on the global claim counter
+#endif
+#ifndef PB_SKIP_LIFT
+#define PB_SKIP_LIFT 0     // timing experiments only: 1 = decode + hand-off, no lifting
+#endif
 constexpr int kFusedWarps = PB_FUSED_WARPS;
 
 struct FusedParams {
@@ -120,7 +126,12 @@ __device__ __forceinline__ bool publish(const FusedParams& p, int m, int f, cons
 
 __device__ __forceinline__ void lift_if_last(const FusedParams& p, bool last, int f, int lane) {
   if (!last) return;
+#if PB_SKIP_LIFT
+  for (int jj = lane; jj < p.J; jj += 32)
+    for (int v = 0; v < p.V; ++v) p.records[((size_t)f * p.V + v) * p.J + jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+#else
   for (int jj = lane; jj < p.J; jj += 32) lift_frame_joint(p, f, jj);
+#endif
   if (lane == 0) p.ws[4 + f] = 0;
 }
 
@@ -163,25 +174,51 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 4) lift_fused_kernel(const F
 __global__ void __launch_bounds__(kFusedWarps * 32, PB_FUSED_MIN_BLOCKS) lift_fused_tma_kernel(const FusedParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
-  const int J = p.J, V = p.V, H = p.H, W = p.W;
+  const int J = p.J, V = p.V;
   const int total = p.B * V * J;
-  Affine6 aff;
+  int batch_next = 0, batch_left = 0;  // warp-uniform: maps left of the batch claimed last
   stream_maps_tma(
-      smem_raw, kFusedWarps, p.hv, J, H * W, total,
-      [&]() { return __shfl_sync(0xffffffffu, claim(p, lane), 0); },
-      [&](int m) { aff = load_affine(p.affine + 6 * (size_t)(m / J)); },
-      [&](int m, const float* base, ArgMax am) {
-        const DecodeOut o = finish_map(am, base, H, W, true, aff, p.post_process != 0);
-        const int f = (m / J) / V;
-        lift_if_last(p, publish(p, m, f, o, lane), f, lane);
+      smem_raw, kFusedWarps, p.hv, J, p.H, p.W, total, p.affine, p.post_process != 0,
+      [&]() {
+        if (batch_left == 0) {
+          int m0 = 0;
+          if (lane == 0) m0 = atomicAdd(p.ws, PB_CLAIM_BATCH);
+          batch_next = __shfl_sync(0xffffffffu, m0, 0);
+          batch_left = PB_CLAIM_BATCH;
+        }
+        --batch_left;
+        const int m = batch_next++;
+        return m < total ? m : total;
+      },
+      [&](int m, const DecodeOut& o) {  // publish: stores + the arrival atomic are issued, not awaited
+        int old = 0;
+        if (lane == 0) {
+          reinterpret_cast<float2*>(p.out_xy)[m] = make_float2(o.x, o.y);
+          p.out_maxval[m] = o.maxval;
+          if (p.out_idx) p.out_idx[m] = o.idx;
+          p.records[m] = make_float4(o.x, o.y, o.maxval, __int_as_float(1));
+          old = atomicAdd(p.ws + 4 + (m / J) / V, 1);
+        }
+        return old;
+      },
+      [&](int m, int old) {             // complete: the warp that saw the last arrival lifts the frame
+        const bool last = __shfl_sync(0xffffffffu, old, 0) == V * J - 1;
+        lift_if_last(p, last, (m / J) / V, lane);
       });
   block_exit(p);
 }
 
 int fill_views(const float* const* hm_views_host, int n_ptr, int N, HmViews& hv);
 bool views_vec_ok(const HmViews& hv, int HW);
+int launch_decode(const HmViews& hv, int N, int J, int H, int W, const double* affine, int post_process,
+                  float* out_xy, float* out_maxval, int32_t* out_idx, void* stream);
+int launch_lift_after_decode(const double* campack, const int32_t* cam_index, const float* xy,
+                             const float* maxval, int use_conf, float conf_thre, int B, int V, int J,
+                             int no_dist, double* out_X, float* out_err32, double* out_proj, void* stream);
 
-static int g_lift_variant = 1;
+// 2 = two kernels (decode, then one thread per (frame, joint)); measured faster than either fused
+// kernel on B200 because lifting inside the streaming warps steals their time (profiles/)
+static int g_lift_variant = 2;
 
 }  // namespace pb200
 
@@ -189,7 +226,7 @@ using namespace pb200;
 
 extern "C" int pb200_set_tuning(int key, int value) {
   PB_REQUIRE(key == PB200_TUNE_LIFT_VARIANT, "unknown tuning key %d", key);
-  PB_REQUIRE(value == 0 || value == 1, "lift variant must be 0 (LDG) or 1 (TMA ring)");
+  PB_REQUIRE(value >= 0 && value <= 2, "lift variant must be 0 (fused, LDG), 1 (fused, TMA ring) or 2 (two kernels)");
   g_lift_variant = value;
   return PB200_OK;
 }
@@ -228,6 +265,12 @@ extern "C" int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, in
   p.ws = reinterpret_cast<int32_t*>(workspace);
   const size_t ints = (((size_t)B + 4 + 3) / 4) * 4;
   p.records = reinterpret_cast<float4*>(p.ws + ints);
+  if (g_lift_variant == 2) {
+    rc = launch_decode(p.hv, B * V, J, H, W, affine, post_process, out_xy, out_maxval, out_idx, stream);
+    if (rc != PB200_OK) return rc;
+    return launch_lift_after_decode(campack, cam_index, out_xy, out_maxval, use_conf, conf_thre, B, V, J,
+                                    no_distortion, out_X, out_err, out_proj, stream);
+  }
   const int sm = cached_sm_count();
   if (sm <= 0) return PB200_ERR_CUDA;
   const long long need = ((long long)B * V * J + kFusedWarps - 1) / kFusedWarps;

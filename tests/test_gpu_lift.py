@@ -74,9 +74,9 @@ def test_fused_confidence_threshold_and_unfused_agree():
     assert (ref == 0).all(axis=2).any()                               # some joints had < 2 views
 
 
-@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('variant', [0, 1, 2])
 def test_fused_front_ends_agree(variant):
-    """LDG and TMA-ring front ends are the same arithmetic: identical bits, incl. NaN maps and 80x80."""
+    """Fused-LDG, fused-TMA and the two-kernel path are the same arithmetic: identical bits, incl. NaN maps and 80x80."""
     from pose_unsupervised_b200 import _lib
     from pose_unsupervised_b200.multiviews.triangulate import lift_heatmaps
     try:
@@ -95,17 +95,23 @@ def test_fused_front_ends_agree(variant):
             good = ok.reshape(16, 4, 17).all(axis=1)
             assert np.abs(res.poses3d - pts)[good].max() < 1e-2
     finally:
-        _lib.call('pb200_set_tuning', 1, 1)
+        _lib.call('pb200_set_tuning', 1, 2)
 
 
-def test_fused_repeated_launches_leave_workspace_clean():
+@pytest.mark.parametrize('variant', [1, 2])
+def test_fused_repeated_launches_leave_workspace_clean(variant):
+    from pose_unsupervised_b200 import _lib
     from pose_unsupervised_b200.multiviews.triangulate import lift_heatmaps
     hm, center, scale, cams = _inputs(64, 4, 17, 64, seed=9)
     d_hm = torch.from_numpy(hm).cuda()
-    first = lift_heatmaps(d_hm, center, scale, cams)
-    for _ in range(5):
-        again = lift_heatmaps(d_hm, center, scale, cams)
-        assert torch.equal(first.poses3d, again.poses3d) and torch.equal(first.reproj_err, again.reproj_err)
+    _lib.call('pb200_set_tuning', 1, variant)
+    try:
+        first = lift_heatmaps(d_hm, center, scale, cams)
+        for _ in range(5):
+            again = lift_heatmaps(d_hm, center, scale, cams)
+            assert torch.equal(first.poses3d, again.poses3d) and torch.equal(first.reproj_err, again.reproj_err)
+    finally:
+        _lib.call('pb200_set_tuning', 1, 2)
     views = [d_hm.view(64, 4, 17, 64, 64)[:, v].contiguous() for v in range(4)]
     listed = lift_heatmaps(views, center, scale, cams)
     assert torch.equal(first.poses3d, listed.poses3d) and torch.equal(first.xy, listed.xy)
