@@ -82,6 +82,19 @@ int pb200_decode(const float* const* hm_views_host, int n_ptr, int N, int J, int
                  const double* affine, int post_process,
                  float* out_xy, float* out_maxval, int32_t* out_idx, void* stream);
 
+/* Flip-test averaging fused with the decode: replaces lib/core/function.py:567-583 (flip_back_th,
+ * TEST.SHIFT_HEATMAP, (view + view_flipped) * 0.5) followed by get_final_preds (:632-640).
+ *   hm_views_host / hm_flip_views_host : the plain and the mirrored-input network outputs
+ *               (n_ptr tensors each, as in pb200_decode)
+ *   joint_src [J] int32 (device) : joint whose flipped map feeds joint j (j itself, or its
+ *               left/right partner from dataset.flip_pairs)
+ *   out_avg   [N,J,H,W] float32 : the averaged heatmaps, view-minor rows (what validate() stores)
+ */
+int pb200_decode_flip(const float* const* hm_views_host, const float* const* hm_flip_views_host,
+                      int n_ptr, int N, int J, int H, int W, const int32_t* joint_src, int shift_heatmap,
+                      const double* affine, int post_process,
+                      float* out_avg, float* out_xy, float* out_maxval, int32_t* out_idx, void* stream);
+
 /* Replaces utils.transforms.transform_preds (lib/utils/transforms.py:67-73) on already
  * decoded heatmap coordinates: out[n,j] = [x, y, 1] @ affine[n].T in float64.
  *   coords [N,J,2] (coords_dtype), affine [N,6] float64 -> out [N,J,2] float64
@@ -145,6 +158,21 @@ int pb200_ransac(const double* campack, const int32_t* cam_index, const void* xy
 int pb200_epipolar(const double* fmat, const int32_t* subj_index, const void* xy, int xy_dtype,
                    const void* weight, int w_dtype, int B, int V, int J,
                    double* out_resid, double* out_sum, void* stream);
+
+/* Exact fundamental matrices from calibrated cameras, F = K_b^-T [t]x R K_a^-1 (unit Frobenius
+ * norm), so that x_b^T F x_a = 0 for pin-hole projections: replaces the offline LMedS estimate
+ * of run/test/generate_fundamental_matirx.py:45-57.  cam_a / cam_b [n] int32 ids into campack
+ * -> out_F [n,9] float64.
+ */
+int pb200_fundamental(const double* campack, const int32_t* cam_a, const int32_t* cam_b, int n,
+                      double* out_F, void* stream);
+
+/* break_limb_length of run/pose3d/estimate.py:84-96: out_flag[f] = 1 iff some limb of pose f
+ * deviates from its expected length by more than thres * expected.  poses [B,J,3] float64,
+ * edges [E,2] int32, limb [B,E] (limb_per_frame = 1) or [E] float64 -> out_flag [B] uint8.
+ */
+int pb200_limb_break(const double* poses, const int32_t* edges, const double* limb, int limb_per_frame,
+                     int B, int J, int E, double thres, uint8_t* out_flag, void* stream);
 
 /* ---- MPJPE partial sums -----------------------------------------------------------
  * run/test/test_triangulate.py:98-101: norm = |pred - gt| over [B,J];

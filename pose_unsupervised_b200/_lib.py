@@ -29,6 +29,8 @@ _PROTOS = {
                                   c_void_p, c_void_p]),
     'pb200_decode': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
+    'pb200_decode_flip': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                  c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'pb200_transform_preds': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'pb200_project': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'pb200_frame_change': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
@@ -40,6 +42,8 @@ _PROTOS = {
                              c_int, c_double, c_int, c_void_p, c_void_p]),
     'pb200_epipolar': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                c_int, c_void_p, c_void_p, c_void_p]),
+    'pb200_fundamental': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    'pb200_limb_break': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, c_void_p]),
     'pb200_mpjpe_stats': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'pb200_lift_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'pb200_set_tuning': (c_int, [c_int, c_int]),

@@ -58,6 +58,42 @@ def decode_heatmaps(heatmaps, center=None, scale=None, post_process=False, retur
     return (xy, maxvals, idx) if return_idx else (xy, maxvals)
 
 
+def decode_heatmaps_flip(heatmaps, heatmaps_flipped, flip_pairs, shift_heatmap=True, center=None,
+                         scale=None, post_process=False, return_idx=False):
+    """Flip-test averaging + decode in one pass (lib/core/function.py:567-583, 632-640).
+
+    heatmaps / heatmaps_flipped : the network output for the input and for the mirrored input
+               (one [N,J,H,W] tensor or a list of V per-view tensors, like decode_heatmaps)
+    flip_pairs : dataset.flip_pairs, e.g. [[0, 5], [1, 4], ...] (left/right joints to swap back)
+    Returns (avg [N,J,H,W] float32 view-minor, xy [N,J,2], maxvals [N,J][, idx]) as CUDA tensors;
+    avg equals ``(view + shift(flip_back_th(view_flipped))) * 0.5`` bit for bit.
+    """
+    rt.require_device()
+    views, N, J, H, W = _view_pointers(heatmaps)
+    fviews, Nf, Jf, Hf, Wf = _view_pointers(heatmaps_flipped)
+    if (len(fviews), Nf, Jf, Hf, Wf) != (len(views), N, J, H, W):
+        raise ValueError('heatmaps and heatmaps_flipped must have the same layout')
+    src = np.arange(J, dtype=np.int32)
+    for a, b in flip_pairs:
+        src[a], src[b] = b, a
+    d_src = rt.to_device(src)
+    affine = None
+    if center is not None:
+        affine = crop_affine(center, scale, (W, H), inv=1)
+        if affine.shape[0] != N:
+            raise ValueError('center/scale have %d rows, heatmaps %d' % (affine.shape[0], N))
+    avg = rt.empty((N, J, H, W), torch.float32)
+    xy = rt.empty((N, J, 2), torch.float32)
+    maxvals = rt.empty((N, J), torch.float32)
+    idx = rt.empty((N, J), torch.int32) if return_idx else None
+    p1 = (ctypes.c_void_p * len(views))(*[v.data_ptr() for v in views])
+    p2 = (ctypes.c_void_p * len(views))(*[v.data_ptr() for v in fviews])
+    _lib.call('pb200_decode_flip', p1, p2, len(views), N, J, H, W, rt.ptr(d_src), int(bool(shift_heatmap)),
+              rt.ptr(affine), int(bool(post_process)), rt.ptr(avg), rt.ptr(xy), rt.ptr(maxvals), rt.ptr(idx),
+              rt.stream_ptr())
+    return (avg, xy, maxvals, idx) if return_idx else (avg, xy, maxvals)
+
+
 def get_max_preds(batch_heatmaps):
     """lib/core/inference.py:19-47: (preds [N,J,2] float32 heatmap px, maxvals [N,J,1])."""
     assert isinstance(batch_heatmaps, np.ndarray), 'batch_heatmaps should be numpy.ndarray'

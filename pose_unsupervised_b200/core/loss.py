@@ -30,6 +30,38 @@ class FundamentalTable(object):
                 host[self.slot[s], a, b] = np.asarray(F, dtype=np.float64).reshape(9)
         self.fmat = rt.to_device(host)
 
+    @classmethod
+    def from_cameras(cls, cams_by_subject):
+        """{subject: [V camera dicts]} -> exact F for every ordered view pair, computed on the GPU
+        (replaces run/test/generate_fundamental_matirx.py, which fits F to data with LMedS)."""
+        from ..multiviews.cameras import pack_camera
+        rt.require_device()
+        subjects = sorted(cams_by_subject)
+        nviews = len(cams_by_subject[subjects[0]])
+        pack = np.stack([pack_camera(c) for s in subjects for c in cams_by_subject[s]])
+        ia, ib = [], []
+        for si in range(len(subjects)):
+            for a in range(nviews):
+                for b in range(nviews):
+                    ia.append(si * nviews + a)
+                    ib.append(si * nviews + b)
+        d_pack = rt.to_device(pack)
+        d_a, d_b = rt.to_device(np.array(ia, dtype=np.int32)), rt.to_device(np.array(ib, dtype=np.int32))
+        F = rt.empty((len(ia), 9), torch.float64)
+        _lib.call('pb200_fundamental', rt.ptr(d_pack), rt.ptr(d_a), rt.ptr(d_b), len(ia), rt.ptr(F),
+                  rt.stream_ptr())
+        self = cls.__new__(cls)
+        self.slot = {s: i for i, s in enumerate(subjects)}
+        self.nviews = nviews
+        self.fmat = F.view(len(subjects), nviews, nviews, 9).contiguous()
+        return self
+
+    def as_dict(self):
+        """{(subject, a, b): F[3,3]} like the reference's fundamental_matrix.pkl (a != b)."""
+        host = self.fmat.cpu().numpy()
+        return {(s, a, b): host[i, a, b].reshape(3, 3) for s, i in self.slot.items()
+                for a in range(self.nviews) for b in range(self.nviews) if a != b}
+
     def slots(self, subjects):
         subs = subjects.tolist() if hasattr(subjects, 'tolist') else list(subjects)
         return rt.to_device(np.array([self.slot[s] for s in subs], dtype=np.int32))

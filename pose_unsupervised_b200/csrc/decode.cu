@@ -198,3 +198,74 @@ extern "C" int pb200_transform_preds(const void* coords, int coords_dtype, const
   PB_LAUNCH_CHECK("transform_preds_kernel");
   return PB200_OK;
 }
+
+// ---- flip-test averaging fused with the decode (lib/core/function.py:567-583 + :632-640) ----------
+// validate() runs the network on the mirrored input, flips the result back (mirror the columns, swap
+// left/right joints), optionally shifts it one column to the right (TEST.SHIFT_HEATMAP) and averages
+// it with the plain output before decoding.  Here one warp per (row, joint) reads both maps once,
+// writes the averaged map (it is also what goes into the h5 file, function.py:640,673) and decodes it
+// on the fly -- instead of flip / index_select / clone / add / mul kernels plus a second pass.
+namespace pb200 {
+__global__ void __launch_bounds__(256)
+decode_flip_kernel(HmViews hv, HmViews hf, int N, int J, int H, int W, const int32_t* __restrict__ joint_src,
+                   int shift, const double* __restrict__ affine, int post_process,
+                   float* __restrict__ out_avg, float* __restrict__ out_xy, float* __restrict__ out_maxval,
+                   int32_t* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long total = (long long)N * J;
+  const int HW = H * W;
+  for (long long m = (long long)blockIdx.x * 8 + warp; m < total; m += (long long)gridDim.x * 8) {
+    const int row = (int)(m / J), j = (int)(m % J);
+    const float* a = map_base(hv, row, j, J, HW);
+    const float* b = map_base(hf, row, joint_src[j], J, HW);
+    float* o = out_avg + (size_t)m * HW;
+    float best = -INFINITY;
+    int bidx = lane < HW ? lane : 0x7fffffff;
+    for (int e = lane; e < HW; e += 32) {
+      const int y = e / W, x = e - y * W;
+      // flipped-back column x reads raw column W-1-x; shifted right by one it reads W-x (x >= 1)
+      const int xs = shift ? (x >= 1 ? W - x : W - 1) : W - 1 - x;
+      const float v = (__ldg(a + e) + __ldg(b + y * W + xs)) * 0.5f;
+      o[e] = v;
+      const bool best_nan = best != best;
+      if (!best_nan && ((v > best) || (v != v))) { best = v; bidx = e; }
+    }
+    const ArgMax am = warp_argmax<true>(best, bidx);
+    __syncwarp();  // the averaged map is read back for the quarter-pixel shift
+    Affine6 aff;
+    if (affine) aff = load_affine(affine + 6 * (size_t)row);
+    const DecodeOut r = finish_map<false>(am, o, H, W, affine != nullptr, aff, post_process != 0);
+    if (lane == 0) {
+      reinterpret_cast<float2*>(out_xy)[m] = make_float2(r.x, r.y);
+      out_maxval[m] = r.maxval;
+      if (out_idx) out_idx[m] = r.idx;
+    }
+  }
+}
+}  // namespace pb200
+
+extern "C" int pb200_decode_flip(const float* const* hm_views_host, const float* const* hm_flip_views_host,
+                                 int n_ptr, int N, int J, int H, int W, const int32_t* joint_src,
+                                 int shift_heatmap, const double* affine, int post_process,
+                                 float* out_avg, float* out_xy, float* out_maxval, int32_t* out_idx,
+                                 void* stream) {
+  PB_REQUIRE(N >= 0 && J >= 1 && H >= 1 && W >= 1, "bad shape N=%d J=%d H=%d W=%d", N, J, H, W);
+  PB_REQUIRE((long long)H * W < (1LL << 24), "map of %dx%d exceeds the float32-exact index range", H, W);
+  if (N == 0) return PB200_OK;
+  PB_REQUIRE(joint_src && out_avg && out_xy && out_maxval, "null pointer");
+  HmViews hv, hf;
+  int rc = fill_views(hm_views_host, n_ptr, N, hv);
+  if (rc != PB200_OK) return rc;
+  rc = fill_views(hm_flip_views_host, n_ptr, N, hf);
+  if (rc != PB200_OK) return rc;
+  const long long maps = (long long)N * J;
+  const int sm = cached_sm_count();
+  if (sm <= 0) return PB200_ERR_CUDA;
+  long long blocks = (maps + 7) / 8;
+  const long long cap = (long long)sm * 8;
+  if (blocks > cap) blocks = cap;
+  decode_flip_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      hv, hf, N, J, H, W, joint_src, shift_heatmap, affine, post_process, out_avg, out_xy, out_maxval, out_idx);
+  PB_LAUNCH_CHECK("decode_flip_kernel");
+  return PB200_OK;
+}

@@ -152,7 +152,10 @@ __device__ __forceinline__ Affine6 load_affine(const double* __restrict__ trans)
 }
 
 // Coordinates from the argmax: mask, quarter-pixel shift, inverse crop affine.
-__device__ __forceinline__ DecodeOut finish_map(const ArgMax am, const float* __restrict__ base, int H,
+// kReadOnly: the map was not written by this kernel, so the neighbour loads may use the
+// non-coherent read-only path (__ldg).
+template <bool kReadOnly = true>
+__device__ __forceinline__ DecodeOut finish_map(const ArgMax am, const float* base, int H,
                                                 int W, bool has_trans, const Affine6& a,
                                                 bool post_process) {
   DecodeOut o;
@@ -166,8 +169,15 @@ __device__ __forceinline__ DecodeOut finish_map(const ArgMax am, const float* __
       const int px = (int)floorf(fx + 0.5f), py = (int)floorf(fy + 0.5f);
       if (1 < px && px < W - 1 && 1 < py && py < H - 1) {
         const float* c = base + py * W + px;
-        const float dx = __ldg(c + 1) - __ldg(c - 1);
-        const float dy = __ldg(c + W) - __ldg(c - W);
+        float dx, dy;
+        if (kReadOnly) {
+          dx = __ldg(c + 1) - __ldg(c - 1);
+          dy = __ldg(c + W) - __ldg(c - W);
+        } else {
+          const volatile float* vc = c;
+          dx = vc[1] - vc[-1];
+          dy = vc[W] - vc[-W];
+        }
         // np.sign: -1, 0, +1, NaN for NaN
         const float sx = dx > 0.f ? 1.f : (dx < 0.f ? -1.f : (dx == 0.f ? 0.f : dx));
         const float sy = dy > 0.f ? 1.f : (dy < 0.f ? -1.f : (dy == 0.f ? 0.f : dy));

@@ -318,3 +318,89 @@ extern "C" int pb200_frame_change(const double* R, const double* T, const double
   PB_LAUNCH_CHECK("frame_change_kernel");
   return PB200_OK;
 }
+
+// ---- fundamental matrices from calibrated cameras -----------------------------------------------
+// The reference estimates F per (subject, view pair) from data with cv2.findFundamentalMat (LMedS,
+// run/test/generate_fundamental_matirx.py:45-57) so that x_b^T F x_a ~ 0.  With calibrated cameras F
+// is exact:  F = K_b^-T [t]x R K_a^-1,  R = R_b R_a^T,  t = R_b (C_a - C_b), scaled to unit Frobenius
+// norm.  One thread per ordered pair.
+namespace pb200 {
+__global__ void fundamental_kernel(const double* __restrict__ campack, const int32_t* __restrict__ cam_a,
+                                   const int32_t* __restrict__ cam_b, int n, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Cam a, b;
+  load_cam(campack + (size_t)cam_a[i] * PB200_CAM_STRIDE, a);
+  load_cam(campack + (size_t)cam_b[i] * PB200_CAM_STRIDE, b);
+  double R[9], t[3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      R[3 * r + c] = b.R[3 * r] * a.R[3 * c] + b.R[3 * r + 1] * a.R[3 * c + 1] + b.R[3 * r + 2] * a.R[3 * c + 2];
+  const double d[3] = {a.T[0] - b.T[0], a.T[1] - b.T[1], a.T[2] - b.T[2]};
+  for (int r = 0; r < 3; ++r) t[r] = b.R[3 * r] * d[0] + b.R[3 * r + 1] * d[1] + b.R[3 * r + 2] * d[2];
+  // E = [t]x R
+  double E[9];
+  for (int c = 0; c < 3; ++c) {
+    E[c] = -t[2] * R[3 + c] + t[1] * R[6 + c];
+    E[3 + c] = t[2] * R[c] - t[0] * R[6 + c];
+    E[6 + c] = -t[1] * R[c] + t[0] * R[3 + c];
+  }
+  // K^-1 = [[1/fx, 0, -cx/fx], [0, 1/fy, -cy/fy], [0, 0, 1]]
+  const double kb[9] = {1.0 / b.fx, 0, -b.cx / b.fx, 0, 1.0 / b.fy, -b.cy / b.fy, 0, 0, 1};
+  const double ka[9] = {1.0 / a.fx, 0, -a.cx / a.fx, 0, 1.0 / a.fy, -a.cy / a.fy, 0, 0, 1};
+  double T1[9], F[9];
+  for (int r = 0; r < 3; ++r)  // K_b^-T E
+    for (int c = 0; c < 3; ++c)
+      T1[3 * r + c] = kb[r] * E[c] + kb[3 + r] * E[3 + c] + kb[6 + r] * E[6 + c];
+  double nrm = 0.0;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      F[3 * r + c] = T1[3 * r] * ka[c] + T1[3 * r + 1] * ka[3 + c] + T1[3 * r + 2] * ka[6 + c];
+      nrm += F[3 * r + c] * F[3 * r + c];
+    }
+  nrm = sqrt(nrm);
+  for (int k = 0; k < 9; ++k) out[9 * (size_t)i + k] = F[k] / nrm;
+}
+
+// flag[f] = 1 iff some limb of pose f deviates from its expected length by more than thres * expected
+// (run/pose3d/estimate.py:84-96, the trigger of the "combination" mode)
+__global__ void limb_break_kernel(const double* __restrict__ poses, const int32_t* __restrict__ edges,
+                                  const double* __restrict__ limb, int limb_per_frame, int B, int J, int E,
+                                  double thres, uint8_t* __restrict__ flag) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= B) return;
+  const double* p = poses + (size_t)f * J * 3;
+  const double* L = limb + (limb_per_frame ? (size_t)f * E : 0);
+  bool bad = false;
+  for (int e = 0; e < E; ++e) {
+    const double* a = p + 3 * edges[2 * e];
+    const double* c = p + 3 * edges[2 * e + 1];
+    const double dx = a[0] - c[0], dy = a[1] - c[1], dz = a[2] - c[2];
+    const double len = sqrt(dx * dx + dy * dy + dz * dz);
+    if (fabs(L[e] - len) > thres * L[e]) bad = true;
+  }
+  flag[f] = bad ? 1 : 0;
+}
+}  // namespace pb200
+
+extern "C" int pb200_fundamental(const double* campack, const int32_t* cam_a, const int32_t* cam_b, int n,
+                                 double* out_F, void* stream) {
+  PB_REQUIRE(campack && cam_a && cam_b && out_F, "null pointer");
+  PB_REQUIRE(n >= 0, "bad n");
+  if (n == 0) return PB200_OK;
+  pb200::fundamental_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(campack, cam_a, cam_b, n, out_F);
+  PB_LAUNCH_CHECK("fundamental_kernel");
+  return PB200_OK;
+}
+
+extern "C" int pb200_limb_break(const double* poses, const int32_t* edges, const double* limb,
+                                int limb_per_frame, int B, int J, int E, double thres, uint8_t* out_flag,
+                                void* stream) {
+  PB_REQUIRE(poses && edges && limb && out_flag, "null pointer");
+  PB_REQUIRE(B >= 0 && J >= 2 && E >= 1, "bad shape");
+  if (B == 0) return PB200_OK;
+  pb200::limb_break_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(poses, edges, limb, limb_per_frame,
+                                                                         B, J, E, thres, out_flag);
+  PB_LAUNCH_CHECK("limb_break_kernel");
+  return PB200_OK;
+}

@@ -169,3 +169,57 @@ def rpsm(cams, heatmaps, boxes, grid_center, limb_length, pairwise_constraint, c
     return rpsm_batch(list(cams), hm[None], centers, scales,
                       np.asarray(grid_center, dtype=np.float64).reshape(1, 3), limb,
                       pairwise_constraint, config, body)[0]
+
+
+def break_limb_length(poses3d, limb_length, body=None, thres=0.4):
+    """run/pose3d/estimate.py:84-96 for a batch: flag [B] uint8, 1 where some limb of the pose
+    deviates from its expected length by more than ``thres`` x expected.
+
+    limb_length: [E] (one template) or [B,E] in ``body.edges()`` order, or the reference's dict.
+    """
+    rt.require_device()
+    body = HumanBody() if body is None else body
+    edges, _, _ = body.tree_arrays()
+    p = rt.to_device(poses3d, torch.float64)
+    B, J = int(p.shape[0]), int(p.shape[1])
+    if isinstance(limb_length, dict):
+        limb_length = np.array([limb_length[e] for e in body.edges()], dtype=np.float64)
+    L = rt.to_device(limb_length, torch.float64)
+    per_frame = int(L.dim() == 2)
+    flag = rt.empty((B,), torch.uint8)
+    _lib.call('pb200_limb_break', rt.ptr(p), rt.ptr(rt.to_device(edges)), rt.ptr(L), per_frame, B, J,
+              len(edges), float(thres), rt.ptr(flag), rt.stream_ptr())
+    return flag if rt.is_device_tensor(poses3d) else rt.to_host(flag)
+
+
+def lift_combination(cams, heatmaps, boxes_center, boxes_scale, poses2d, limb_lengths, pairwise, config,
+                     body=None, joints_vis=None, thres=0.4):
+    """The "combination" estimator sketched in run/pose3d/estimate.py:229-244: triangulate every
+    frame; where a limb of the triangulated pose breaks its expected length by more than ``thres``
+    the frame is re-estimated by RPSM with the triangulated root joint as grid centre.
+
+    heatmaps [B,V,J,H,W]; poses2d [B*V,J,2] (e.g. decoded from the same heatmaps); limb_lengths
+    [B,E] or [E].  Returns (poses3d [B,J,3] float64 numpy, used_rpsm [B] bool numpy).
+    """
+    from .triangulate import triangulate_poses
+    body = HumanBody() if body is None else body
+    table = CameraTable.from_cameras(cams)
+    hm = rt.to_device(heatmaps)
+    B, V = int(hm.shape[0]), int(hm.shape[1])
+    poses = triangulate_poses(table, rt.to_device_float(poses2d),
+                              None if joints_vis is None else rt.to_device(joints_vis), nviews=V)
+    L = rt.to_device(np.asarray(limb_lengths, dtype=np.float64) if not isinstance(limb_lengths, torch.Tensor)
+                     else limb_lengths, torch.float64)
+    flag = break_limb_length(poses, L, body, thres).bool()
+    sel = torch.nonzero(flag).reshape(-1)
+    if sel.numel() > 0:
+        rows = (sel[:, None] * V + torch.arange(V, device=sel.device)[None]).reshape(-1)
+        sub_table = CameraTable(table.pack, table.index[rows].contiguous())
+        c = rt.to_device_float(boxes_center).reshape(B * V, 2)[rows]
+        s = rt.to_device_float(boxes_scale).reshape(B * V, 2)[rows]
+        limb_sel = L[sel] if L.dim() == 2 else L[None].expand(sel.numel(), -1).contiguous()
+        fixed = rpsm_batch(sub_table, hm[sel].contiguous(), c, s, poses[sel, body.root_idx].contiguous(),
+                           limb_sel, pairwise, config, body)
+        poses = poses.clone()
+        poses[sel] = fixed
+    return rt.to_host(poses), rt.to_host(flag)

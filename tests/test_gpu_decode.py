@@ -121,3 +121,29 @@ def test_full_size_properties(inf):
     assert torch.equal(xy[..., 0], (idx % 64).float()) and torch.equal(xy[..., 1], (idx // 64).float())
     sl = slice(5000, 5064)
     assert np.array_equal(idx[sl].cpu().numpy(), oinf.flat_argmax(hm[sl].cpu().numpy()))
+
+
+@pytest.mark.parametrize('shift', [True, False])
+def test_flip_test_fusion_matches_torch_recipe(inf, shift):
+    """validate()'s flip test (lib/core/function.py:567-583) restated with the reference's own torch ops."""
+    rng = np.random.default_rng(3)
+    B, V, J, hw = 6, 4, 16, 64
+    flip_pairs = [[0, 5], [1, 4], [2, 3], [10, 15], [11, 14], [12, 13]]
+    out = [torch.from_numpy(rng.random((B, J, hw, hw), dtype=np.float32)).cuda() for _ in range(V)]
+    out_f = [torch.from_numpy(rng.random((B, J, hw, hw), dtype=np.float32)).cuda() for _ in range(V)]
+    center = rng.uniform(400, 600, (B * V, 2))
+    scale = np.repeat(rng.uniform(1.5, 3.0, (B * V, 1)), 2, axis=1)
+    # reference recipe
+    order = list(range(J))
+    for a, b in flip_pairs:
+        order[a], order[b] = b, a
+    fb = [torch.index_select(torch.flip(v, dims=[3]), 1, torch.tensor(order).cuda()) for v in out_f]
+    if shift:
+        for v in fb:
+            v[:, :, :, 1:] = v.clone()[:, :, :, 0:-1]
+    ref = [(a + b) * 0.5 for a, b in zip(out, fb)]
+    ref_rows = torch.stack(ref, dim=1).reshape(B * V, J, hw, hw)            # preds[k::nviews] layout
+    avg, xy, mv, idx = inf.decode_heatmaps_flip(out, out_f, flip_pairs, shift, center, scale, True, return_idx=True)
+    assert torch.equal(avg, ref_rows)
+    xy2, mv2, idx2 = inf.decode_heatmaps(ref_rows, center, scale, post_process=True, return_idx=True)
+    assert torch.equal(idx, idx2) and torch.equal(mv, mv2) and torch.equal(xy, xy2)

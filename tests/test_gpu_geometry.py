@@ -160,3 +160,58 @@ def test_pseudo_label_pipeline_full_size(tri):
     cams = [rigs[subj[i]][v] for i in range(sl.start, sl.stop) for v in range(4)]
     ref = otri.triangulate_poses(cams, noisy[sl.start * 4:sl.stop * 4])
     assert np.abs(pts[sl] - ref).max() < TOL_MM
+
+
+def test_fundamental_from_cameras_vs_oracle():
+    from pose_unsupervised_b200.core.loss import FundamentalTable, epipolar_residuals
+    rigs = synth.camera_table(3, 4, seed=31)
+    table = FundamentalTable.from_cameras({s: rigs[s] for s in range(3)})
+    ref = oepi.fundamental_table({s: rigs[s] for s in range(3)})
+    got = table.as_dict()
+    assert set(got) == set(ref)
+    for k in ref:
+        assert np.abs(got[k] - ref[k]).max() < 1e-12
+    poses = synth.random_poses(9, seed=32)
+    subj = np.arange(9) % 3
+    obs, _ = synth.multiview_observations(poses, rigs, subj, distorted=False)
+    assert epipolar_residuals(obs, subj, table).max() < 1e-9
+
+
+def test_break_limb_length_and_combination():
+    from pose_unsupervised_b200.multiviews import pictorial
+    from pose_unsupervised_b200.multiviews.body import HumanBody
+    from tests.util import rpsm_config
+    body = HumanBody.h36m17()
+    edges = body.edges()
+    B = 6
+    poses = synth.random_poses(B, seed=41)
+    limbs = np.array([[np.linalg.norm(p[a] - p[b]) for a, b in edges] for p in poses])
+    broken = poses.copy()
+    broken[1, 3] += [0, 0, 400.0]                 # right ankle of frame 1 far away
+    broken[4, 13] += [300.0, 0, 0]                # left wrist of frame 4
+    flag = pictorial.break_limb_length(broken, limbs, body)
+    ref = np.array([any(abs(limbs[f, e] - np.linalg.norm(broken[f, a] - broken[f, b])) > 0.4 * limbs[f, e]
+                        for e, (a, b) in enumerate(edges)) for f in range(B)])
+    assert np.array_equal(flag.astype(bool), ref) and ref.tolist() == [False, True, False, False, True, False]
+    # combination mode: corrupt one view's 2D joint so triangulation breaks a limb -> RPSM repairs it
+    rig = synth.camera_ring(4, seed=42)
+    cams = [rig[v] for _ in range(B) for v in range(4)]
+    obs, _ = synth.multiview_observations(poses, [rig], [0] * B, noise_px=0.5, seed=43)
+    obs[2 * 4 + 1, 6] += [250.0, -180.0]          # frame 2, view 1, left ankle
+    obs[2 * 4 + 3, 6] += [-220.0, 150.0]
+    hms, centers, scales = [], [], []
+    for f in range(B):
+        boxes = synth.crop_box(rig, poses[f])
+        hms.append(synth.gaussian_heatmaps(rig, boxes, poses[f], 64, 256, 2.0, 0.02, seed=f))
+        centers += [b['center'] for b in boxes]
+        scales += [b['scale'] for b in boxes]
+    avg = {e: float(limbs[:, k].mean()) for k, e in enumerate(edges)}
+    table = pictorial.PairwiseTable.from_limb_lengths(avg, body, 2000, 16)
+    out, used = pictorial.lift_combination(cams, np.array(hms), np.array(centers), np.array(scales), obs, limbs,
+                                           table, rpsm_config(), body)
+    assert used.tolist() == [False, False, True, False, False, False]
+    tri = otri.triangulate_poses(cams, obs)
+    assert np.abs(out[[0, 1, 3, 4, 5]] - tri[[0, 1, 3, 4, 5]]).max() < 1e-2
+    err_tri = np.linalg.norm(tri[2] - poses[2], axis=1).max()
+    err_out = np.linalg.norm(out[2] - poses[2], axis=1).max()
+    assert err_tri > 100.0 and err_out < 60.0
