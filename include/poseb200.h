@@ -174,6 +174,23 @@ int pb200_fundamental(const double* campack, const int32_t* cam_a, const int32_t
 int pb200_limb_break(const double* poses, const int32_t* edges, const double* limb, int limb_per_frame,
                      int B, int J, int E, double thres, uint8_t* out_flag, void* stream);
 
+/* ---- differentiable epipolar term (training-time consumer, lib/core/function.py:298-310) -------
+ * pb200_softargmax_fwd replaces generate_integral_preds_2d_th (lib/utils/transforms.py:149-171):
+ *   p = softmax(beta * hm) per map (beta = 100), out_xy [N,J,2] = (sum p*col, sum p*row) float32,
+ *   out_stats [N,J,2] = (max logit, sum of exp) kept for the backward pass.
+ * pb200_softargmax_bwd: grad_hm [N,J,H,W] = beta * p * ((col - x) * gx + (row - y) * gy).
+ * pb200_epipolar_grad: gradient of sum |x_b^T F x_a| * w_b * w_a * gscale (FundamentalLoss,
+ *   lib/core/loss.py:101-133) with respect to xy, ACCUMULATED into grad_xy [B*V,J,2] float64
+ *   (zero it first).
+ */
+int pb200_softargmax_fwd(const float* hm, int N, int J, int H, int W, float beta, float* out_xy,
+                         float* out_stats, void* stream);
+int pb200_softargmax_bwd(const float* hm, const float* stats, const float* xy, const float* grad_xy,
+                         int N, int J, int H, int W, float beta, float* grad_hm, void* stream);
+int pb200_epipolar_grad(const double* fmat, const int32_t* subj_index, const void* xy, int xy_dtype,
+                        const void* weight, int w_dtype, int B, int V, int J, double gscale,
+                        double* grad_xy, void* stream);
+
 /* ---- MPJPE partial sums -----------------------------------------------------------
  * run/test/test_triangulate.py:98-101: norm = |pred - gt| over [B,J];
  * out[0]+=sum, out[1]+=sum of squares, out[2]=max(out[2],.), out[3]+=count  (float64;

@@ -44,6 +44,11 @@ _PROTOS = {
                                c_int, c_void_p, c_void_p, c_void_p]),
     'pb200_fundamental': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     'pb200_limb_break': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, c_void_p]),
+    'pb200_softargmax_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    'pb200_softargmax_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                     c_void_p, c_void_p]),
+    'pb200_epipolar_grad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                    c_double, c_void_p, c_void_p]),
     'pb200_mpjpe_stats': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'pb200_lift_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'pb200_set_tuning': (c_int, [c_int, c_int]),

@@ -12,7 +12,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.environ.get('PB200_LIB', os.path.join(PKG_DIR, 'libposeb200.so'))   # PB200_LIB: tuning sweeps only
-SOURCES = ['api.cu', 'decode.cu', 'geometry.cu', 'lift_fused.cu', 'rpsm.cu']
+SOURCES = ['api.cu', 'decode.cu', 'geometry.cu', 'lift_fused.cu', 'rpsm.cu', 'softargmax.cu']
 HEADERS = ['pb_common.cuh', 'lift_math.cuh', 'decode.cuh', 'lift.cuh',
            os.path.join('..', '..', 'include', 'poseb200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',

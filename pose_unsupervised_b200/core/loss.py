@@ -92,8 +92,39 @@ def epipolar_residuals(pred2d, subjects, fundamental, nviews=4, weight=None, ret
     return (resid, total) if return_sum else resid
 
 
+class _EpipolarLossFn(torch.autograd.Function):
+    """sum over frames, ordered pairs and joints of |x_b^T F x_a| (* w_b * w_a), times `scale`."""
+
+    @staticmethod
+    def forward(ctx, xy, weight, subj_slots, fmat, nviews, scale):
+        x = xy.detach().contiguous()
+        N, J = int(x.shape[0]), int(x.shape[1])
+        B = N // nviews
+        w = None if weight is None else weight.detach().reshape(N, J).contiguous()
+        resid = rt.empty((B, nviews * (nviews - 1), J), torch.float64)
+        total = rt.zeros((1,), torch.float64)
+        _lib.call('pb200_epipolar', rt.ptr(fmat), rt.ptr(subj_slots), rt.ptr(x), rt.float_dtype_tag(x),
+                  rt.ptr(w), rt.float_dtype_tag(w) if w is not None else _lib.F64, B, nviews, J,
+                  rt.ptr(resid), rt.ptr(total), rt.stream_ptr())
+        ctx.save_for_backward(x, w if w is not None else x.new_empty(0), subj_slots, fmat)
+        ctx.has_w, ctx.nviews, ctx.scale = w is not None, nviews, float(scale)
+        return (total[0] * scale).to(xy.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, w, subj_slots, fmat = ctx.saved_tensors
+        N, J = int(x.shape[0]), int(x.shape[1])
+        B = N // ctx.nviews
+        g = rt.zeros((N, J, 2), torch.float64)
+        _lib.call('pb200_epipolar_grad', rt.ptr(fmat), rt.ptr(subj_slots), rt.ptr(x), rt.float_dtype_tag(x),
+                  rt.ptr(w) if ctx.has_w else None, rt.float_dtype_tag(w) if ctx.has_w else _lib.F64,
+                  B, ctx.nviews, J, ctx.scale, rt.ptr(g), rt.stream_ptr())
+        return (g * grad_out.to(torch.float64)).to(x.dtype), None, None, None, None, None
+
+
 class FundamentalLoss(object):
-    """lib/core/loss.py:89-133 (forward scoring)."""
+    """lib/core/loss.py:89-133, forward and backward (the gradient flows to ``joints_2d_list``;
+    ``target_weight`` is treated as a constant, as in the reference's use)."""
 
     def __init__(self, cfg, fundamental_matrix_dict=None):
         self.use_target_weight = cfg.LOSS.USE_TARGET_WEIGHT_FUND
@@ -116,11 +147,14 @@ class FundamentalLoss(object):
         table = self._tables.get(nviews)
         if table is None:
             table = self._tables[nviews] = FundamentalTable(self.fundamental_matrix_dict, nviews)
-        # view-minor rows: row = sample * V + view
-        xy = torch.stack([p.detach() for p in joints_2d_list], dim=1).reshape(K * nviews, J, 2)
+        # view-minor rows: row = sample * V + view (torch.stack keeps the autograd graph)
+        xy = torch.stack(list(joints_2d_list), dim=1).reshape(K * nviews, J, 2)
+        if not xy.is_cuda:
+            xy = xy.to(rt.device())
         w = None
         if self.use_target_weight:
-            w = torch.stack([t.detach() for t in target_weight], dim=1).reshape(K * nviews, J)
-        _, total = epipolar_residuals(rt.to_device(xy), subject, table, nviews, w, return_sum=True)
+            w = torch.stack([t.detach() for t in target_weight], dim=1).reshape(K * nviews, J).to(xy.device)
+            if w.dtype not in (torch.float32, torch.float64):
+                w = w.to(torch.float32)
         npairs = len(list(itertools.permutations(range(nviews), 2)))
-        return total[0] / (K * npairs * J)
+        return _EpipolarLossFn.apply(xy, w, table.slots(subject), table.fmat, nviews, 1.0 / (K * npairs * J))

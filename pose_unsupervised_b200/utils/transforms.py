@@ -62,3 +62,54 @@ def transform_preds(coords, center, scale, output_size):
     target = np.zeros(coords.shape)
     target[:, :2] = rt.to_host(out)[0]
     return target
+
+
+class _SoftArgmax2D(torch.autograd.Function):
+    """softmax(beta * heatmap) expectation of (column, row): forward and backward are one HBM pass
+    each in libposeb200 (csrc/softargmax.cu)."""
+
+    @staticmethod
+    def forward(ctx, heatmaps, beta):
+        rt.require_device()
+        hm = heatmaps.detach().contiguous()
+        if hm.dtype != torch.float32 or not hm.is_cuda or hm.dim() != 4:
+            raise TypeError('heatmaps must be a CUDA float32 [N, J, h, w] tensor')
+        N, J, H, W = [int(v) for v in hm.shape]
+        xy = torch.empty((N, J, 2), dtype=torch.float32, device=hm.device)
+        stats = torch.empty((N, J, 2), dtype=torch.float32, device=hm.device)
+        _lib.call('pb200_softargmax_fwd', rt.ptr(hm), N, J, H, W, float(beta), rt.ptr(xy), rt.ptr(stats),
+                  rt.stream_ptr())
+        ctx.save_for_backward(hm, stats, xy)
+        ctx.beta = float(beta)
+        return xy
+
+    @staticmethod
+    def backward(ctx, grad_xy):
+        hm, stats, xy = ctx.saved_tensors
+        N, J, H, W = [int(v) for v in hm.shape]
+        g = grad_xy.detach().to(torch.float32).contiguous()
+        grad_hm = torch.empty_like(hm)
+        _lib.call('pb200_softargmax_bwd', rt.ptr(hm), rt.ptr(stats), rt.ptr(xy), rt.ptr(g), N, J, H, W,
+                  ctx.beta, rt.ptr(grad_hm), rt.stream_ptr())
+        return grad_hm, None
+
+
+def generate_integral_preds_2d_th(heatmaps, beta=100.0):
+    """lib/utils/transforms.py:149-171: differentiable soft-argmax, heatmaps [N,J,h,w] -> [N,J,2]
+    (x, y) in heatmap pixels.  ``beta`` is the reference's "multiply by a factor 100"."""
+    return _SoftArgmax2D.apply(heatmaps, beta)
+
+
+def transform_back_th(cfg, joints_2d_list, meta):
+    """lib/utils/transforms.py:174-198: heatmap pixels -> image pixels per view, differentiable.
+    The per-sample inverse crop affines come from the crop-affine kernel (float64, cast to float32
+    like the reference); the tiny [N,J,3] x [N,3,2] product is left to torch so autograd sees it."""
+    results = []
+    w, h = int(cfg.NETWORK.HEATMAP_SIZE[0]), int(cfg.NETWORK.HEATMAP_SIZE[1])
+    for p, m in zip(joints_2d_list, meta):
+        c = m['center'].numpy() if isinstance(m['center'], torch.Tensor) else np.asarray(m['center'])
+        s = m['scale'].numpy() if isinstance(m['scale'], torch.Tensor) else np.asarray(m['scale'])
+        trans = crop_affine(c, s, (w, h), inv=1).to(device=p.device, dtype=torch.float32)   # [N,2,3]
+        ones = torch.ones(p.shape[0], p.shape[1], 1, device=p.device, dtype=p.dtype)
+        results.append(torch.matmul(torch.cat((p, ones), dim=2), trans.transpose(2, 1)))
+    return results

@@ -215,3 +215,66 @@ def test_break_limb_length_and_combination():
     err_tri = np.linalg.norm(tri[2] - poses[2], axis=1).max()
     err_out = np.linalg.norm(out[2] - poses[2], axis=1).max()
     assert err_tri > 100.0 and err_out < 60.0
+
+
+def test_differentiable_epipolar_term_vs_torch_autograd():
+    """The training-time chain of lib/core/function.py:298-310 -- soft-argmax, back-transform,
+    FundamentalLoss -- restated with the reference's torch ops and differentiated by autograd,
+    against the CUDA forward/backward kernels."""
+    import itertools
+    import types
+    from pose_unsupervised_b200.core.loss import FundamentalLoss
+    from pose_unsupervised_b200.utils.transforms import generate_integral_preds_2d_th, transform_back_th
+    torch.manual_seed(0)
+    K, V, J, hw = 5, 4, 16, 64
+    rigs = synth.camera_table(3, 4, seed=51)
+    F = oepi.fundamental_table({s: rigs[s] for s in range(3)})
+    subj = np.array([0, 2, 1, 1, 0])
+    rng = np.random.default_rng(52)
+    hms = [(torch.rand((K, J, hw, hw), device='cuda') * 0.1) for _ in range(V)]
+    for v in range(V):                                   # a soft peak per map
+        py, px = rng.integers(5, hw - 5, (2, K, J))
+        for k in range(K):
+            for j in range(J):
+                hms[v][k, j, py[k, j] - 1:py[k, j] + 2, px[k, j] - 1:px[k, j] + 2] += 0.05
+                hms[v][k, j, py[k, j], px[k, j]] += 0.03
+    meta = [{'center': torch.from_numpy(rng.uniform(400, 600, (K, 2)).astype(np.float32)),
+             'scale': torch.from_numpy(np.repeat(rng.uniform(1.5, 3, (K, 1)), 2, axis=1).astype(np.float32)),
+             'subject': torch.from_numpy(subj)} for _ in range(V)]
+    weight = [torch.from_numpy(rng.random((K, J, 1)).astype(np.float32)).cuda() for _ in range(V)]
+    cfg = types.SimpleNamespace(NETWORK=types.SimpleNamespace(HEATMAP_SIZE=np.array([hw, hw])),
+                                LOSS=types.SimpleNamespace(USE_TARGET_WEIGHT_FUND=True))
+
+    def ref_softargmax(h):                               # lib/utils/transforms.py:149-171
+        n, j, hh, ww = h.shape
+        p = torch.nn.functional.softmax((h * 100).view(n, j, -1), dim=-1).view(n, j, hh, ww)
+        xs = torch.arange(ww, dtype=torch.float32, device=h.device)
+        ys = torch.arange(hh, dtype=torch.float32, device=h.device)
+        return torch.stack([(p.sum(dim=2) * xs.view(1, 1, -1)).sum(dim=2),
+                            (p.sum(dim=3) * ys.view(1, 1, -1)).sum(dim=2)], dim=2)
+
+    def ref_loss(joints, w):                             # lib/core/loss.py:101-133
+        homo = [torch.cat((p, torch.ones(K, J, 1, device=p.device)), dim=2) for p in joints]
+        loss = 0
+        for idx, s in enumerate(subj):
+            for a, b in itertools.permutations(range(V), 2):
+                Fm = torch.from_numpy(F[(int(s), a, b)]).to('cuda', torch.float32)
+                t = torch.abs(torch.sum(torch.mm(homo[b][idx], Fm) * homo[a][idx], dim=1))
+                t = t * torch.squeeze(w[b][idx] * w[a][idx])
+                loss = loss + t.sum()
+        return loss / (K * 12 * J)
+
+    a_in = [h.clone().requires_grad_(True) for h in hms]
+    b_in = [h.clone().requires_grad_(True) for h in hms]
+    ours_xy = [generate_integral_preds_2d_th(h) for h in a_in]
+    ref_xy = [ref_softargmax(h) for h in b_in]
+    for o, r in zip(ours_xy, ref_xy):
+        assert (o - r).abs().max() < 2e-3                # heatmap pixels
+    ours = FundamentalLoss(cfg, F)(transform_back_th(cfg, ours_xy, meta), weight, meta)
+    ref = ref_loss(transform_back_th(cfg, ref_xy, meta), weight)
+    assert abs(float(ours) - float(ref)) < 1e-4 * max(1.0, abs(float(ref)))
+    ours.backward()
+    ref.backward()
+    for o, r in zip(a_in, b_in):
+        scale = r.grad.abs().max()
+        assert scale > 0 and (o.grad - r.grad).abs().max() < 2e-3 * scale
