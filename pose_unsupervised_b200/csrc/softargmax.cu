@@ -22,22 +22,41 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __global__ void __launch_bounds__(256)
-softargmax_fwd_kernel(const float* __restrict__ hm, long long maps, int H, int W, float beta,
+softargmax_fwd_kernel(const float* __restrict__ hm, long long maps, int H, int W, float beta, int vec,
                       float* __restrict__ out_xy, float* __restrict__ out_stats) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int HW = H * W;
   for (long long m = (long long)blockIdx.x * 8 + warp; m < maps; m += (long long)gridDim.x * 8) {
     const float* base = hm + (size_t)m * HW;
     float mx = -INFINITY;
-    for (int e = lane; e < HW; e += 32) mx = fmaxf(mx, base[e] * beta);
-    mx = warp_max(mx);
     float z = 0.f, sx = 0.f, sy = 0.f;
-    for (int e = lane; e < HW; e += 32) {
-      const float p = expf(base[e] * beta - mx);
-      const int y = e / W, x = e - y * W;
-      z += p;
-      sx = fmaf(p, (float)x, sx);
-      sy = fmaf(p, (float)y, sy);
+    if (vec) {  // W % 4 == 0 and 16-byte aligned maps: a float4 never straddles a row
+      const float4* b4 = reinterpret_cast<const float4*>(base);
+      for (int i = lane; i < (HW >> 2); i += 32) {
+        const float4 q = b4[i];
+        mx = fmaxf(mx, fmaxf(fmaxf(q.x * beta, q.y * beta), fmaxf(q.z * beta, q.w * beta)));
+      }
+      mx = warp_max(mx);
+      for (int i = lane; i < (HW >> 2); i += 32) {
+        const float4 q = b4[i];
+        const int e = 4 * i, y = e / W, x = e - y * W;
+        const float p0 = expf(q.x * beta - mx), p1 = expf(q.y * beta - mx), p2 = expf(q.z * beta - mx),
+                    p3 = expf(q.w * beta - mx);
+        const float ps = (p0 + p1) + (p2 + p3);
+        z += ps;
+        sx += ps * (float)x + (p1 + 2.f * p2 + 3.f * p3);
+        sy = fmaf(ps, (float)y, sy);
+      }
+    } else {
+      for (int e = lane; e < HW; e += 32) mx = fmaxf(mx, base[e] * beta);
+      mx = warp_max(mx);
+      for (int e = lane; e < HW; e += 32) {
+        const float p = expf(base[e] * beta - mx);
+        const int y = e / W, x = e - y * W;
+        z += p;
+        sx = fmaf(p, (float)x, sx);
+        sy = fmaf(p, (float)y, sy);
+      }
     }
     z = warp_sum(z);
     sx = warp_sum(sx);
@@ -54,7 +73,7 @@ softargmax_fwd_kernel(const float* __restrict__ hm, long long maps, int H, int W
 __global__ void __launch_bounds__(256)
 softargmax_bwd_kernel(const float* __restrict__ hm, const float* __restrict__ stats,
                       const float* __restrict__ xy, const float* __restrict__ grad_xy, long long maps,
-                      int H, int W, float beta, float* __restrict__ grad_hm) {
+                      int H, int W, float beta, int vec, float* __restrict__ grad_hm) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int HW = H * W;
   for (long long m = (long long)blockIdx.x * 8 + warp; m < maps; m += (long long)gridDim.x * 8) {
@@ -63,10 +82,26 @@ softargmax_bwd_kernel(const float* __restrict__ hm, const float* __restrict__ st
     const float mx = stats[2 * m], rz = 1.0f / stats[2 * m + 1];
     const float x0 = xy[2 * m], y0 = xy[2 * m + 1];
     const float gx = grad_xy[2 * m] * beta, gy = grad_xy[2 * m + 1] * beta;
-    for (int e = lane; e < HW; e += 32) {
-      const float p = expf(base[e] * beta - mx) * rz;
-      const int y = e / W, x = e - y * W;
-      g[e] = p * (((float)x - x0) * gx + ((float)y - y0) * gy);
+    if (vec) {
+      const float4* b4 = reinterpret_cast<const float4*>(base);
+      float4* g4 = reinterpret_cast<float4*>(g);
+      for (int i = lane; i < (HW >> 2); i += 32) {
+        const float4 q = b4[i];
+        const int e = 4 * i, y = e / W, x = e - y * W;
+        const float ty = ((float)y - y0) * gy;
+        float4 o;
+        o.x = expf(q.x * beta - mx) * rz * (((float)x - x0) * gx + ty);
+        o.y = expf(q.y * beta - mx) * rz * (((float)(x + 1) - x0) * gx + ty);
+        o.z = expf(q.z * beta - mx) * rz * (((float)(x + 2) - x0) * gx + ty);
+        o.w = expf(q.w * beta - mx) * rz * (((float)(x + 3) - x0) * gx + ty);
+        g4[i] = o;
+      }
+    } else {
+      for (int e = lane; e < HW; e += 32) {
+        const float p = expf(base[e] * beta - mx) * rz;
+        const int y = e / W, x = e - y * W;
+        g[e] = p * (((float)x - x0) * gx + ((float)y - y0) * gy);
+      }
     }
   }
 }
@@ -118,7 +153,8 @@ extern "C" int pb200_softargmax_fwd(const float* hm, int N, int J, int H, int W,
   if (sm <= 0) return PB200_ERR_CUDA;
   long long blocks = (maps + 7) / 8;
   if (blocks > (long long)sm * 8) blocks = (long long)sm * 8;
-  softargmax_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(hm, maps, H, W, beta, out_xy, out_stats);
+  const int vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(hm) & 15u) == 0);
+  softargmax_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(hm, maps, H, W, beta, vec, out_xy, out_stats);
   PB_LAUNCH_CHECK("softargmax_fwd_kernel");
   return PB200_OK;
 }
@@ -133,8 +169,10 @@ extern "C" int pb200_softargmax_bwd(const float* hm, const float* stats, const f
   if (sm <= 0) return PB200_ERR_CUDA;
   long long blocks = (maps + 7) / 8;
   if (blocks > (long long)sm * 8) blocks = (long long)sm * 8;
+  const int vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(hm) & 15u) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(grad_hm) & 15u) == 0);
   softargmax_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(hm, stats, xy, grad_xy, maps, H, W,
-                                                                         beta, grad_hm);
+                                                                         beta, vec, grad_hm);
   PB_LAUNCH_CHECK("softargmax_bwd_kernel");
   return PB200_OK;
 }
