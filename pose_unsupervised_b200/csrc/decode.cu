@@ -207,8 +207,9 @@ extern "C" int pb200_transform_preds(const void* coords, int coords_dtype, const
 // on the fly -- instead of flip / index_select / clone / add / mul kernels plus a second pass.
 namespace pb200 {
 __global__ void __launch_bounds__(256)
-decode_flip_kernel(HmViews hv, HmViews hf, int N, int J, int H, int W, const int32_t* __restrict__ joint_src,
-                   int shift, const double* __restrict__ affine, int post_process,
+decode_flip_kernel(HmViews hv, HmViews hf, int N, int J, int H, int W, int vec,
+                   const int32_t* __restrict__ joint_src, int shift, const double* __restrict__ affine,
+                   int post_process,
                    float* __restrict__ out_avg, float* __restrict__ out_xy, float* __restrict__ out_maxval,
                    int32_t* __restrict__ out_idx) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -220,16 +221,42 @@ decode_flip_kernel(HmViews hv, HmViews hf, int N, int J, int H, int W, const int
     const float* b = map_base(hf, row, joint_src[j], J, HW);
     float* o = out_avg + (size_t)m * HW;
     float best = -INFINITY;
-    int bidx = lane < HW ? lane : 0x7fffffff;
-    for (int e = lane; e < HW; e += 32) {
-      const int y = e / W, x = e - y * W;
-      // flipped-back column x reads raw column W-1-x; shifted right by one it reads W-x (x >= 1)
-      const int xs = shift ? (x >= 1 ? W - x : W - 1) : W - 1 - x;
-      const float v = (__ldg(a + e) + __ldg(b + y * W + xs)) * 0.5f;
-      o[e] = v;
-      const bool best_nan = best != best;
-      if (!best_nan && ((v > best) || (v != v))) { best = v; bidx = e; }
+    int bidx = 0x7fffffff;
+#define PB_FLIP_UPD(v, e)                                              \
+  {                                                                    \
+    const bool best_nan = best != best;                                \
+    if (bidx == 0x7fffffff || (!best_nan && (((v) > best) || ((v) != (v))))) { best = (v); bidx = (e); } \
+  }
+    if (vec) {  // W % 4 == 0, 16-byte aligned tensors: 128-bit loads and stores
+      const float4* a4 = reinterpret_cast<const float4*>(a);
+      float4* o4 = reinterpret_cast<float4*>(o);
+      for (int i = lane; i < (HW >> 2); i += 32) {
+        const int e = 4 * i, y = e / W, x0 = e - y * W;
+        const float* brow = b + y * W;
+        const float4 q = a4[i];
+        // mirrored columns W-1-x; shifted right by one they become W-x (x >= 1) and W-1 for x = 0
+        const float4 lo = *reinterpret_cast<const float4*>(brow + (W - x0 - 4));   // columns W-x0-4 .. W-x0-1
+        float f0, f1, f2, f3;
+        if (!shift) { f0 = lo.w; f1 = lo.z; f2 = lo.y; f3 = lo.x; }
+        else {
+          f1 = lo.w; f2 = lo.z; f3 = lo.y;
+          f0 = x0 == 0 ? lo.w : __ldg(brow + (W - x0));
+        }
+        float4 r;
+        r.x = (q.x + f0) * 0.5f; r.y = (q.y + f1) * 0.5f; r.z = (q.z + f2) * 0.5f; r.w = (q.w + f3) * 0.5f;
+        o4[i] = r;
+        PB_FLIP_UPD(r.x, e) PB_FLIP_UPD(r.y, e + 1) PB_FLIP_UPD(r.z, e + 2) PB_FLIP_UPD(r.w, e + 3)
+      }
+    } else {
+      for (int e = lane; e < HW; e += 32) {
+        const int y = e / W, x = e - y * W;
+        const int xs = shift ? (x >= 1 ? W - x : W - 1) : W - 1 - x;
+        const float v = (__ldg(a + e) + __ldg(b + y * W + xs)) * 0.5f;
+        o[e] = v;
+        PB_FLIP_UPD(v, e)
+      }
     }
+#undef PB_FLIP_UPD
     const ArgMax am = warp_argmax<true>(best, bidx);
     __syncwarp();  // the averaged map is read back for the quarter-pixel shift
     Affine6 aff;
@@ -264,8 +291,11 @@ extern "C" int pb200_decode_flip(const float* const* hm_views_host, const float*
   long long blocks = (maps + 7) / 8;
   const long long cap = (long long)sm * 8;
   if (blocks > cap) blocks = cap;
+  const int vec = (W % 4 == 0) && views_vec_ok(hv, H * W) && views_vec_ok(hf, H * W) &&
+                  ((reinterpret_cast<uintptr_t>(out_avg) & 15u) == 0);
   decode_flip_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      hv, hf, N, J, H, W, joint_src, shift_heatmap, affine, post_process, out_avg, out_xy, out_maxval, out_idx);
+      hv, hf, N, J, H, W, vec, joint_src, shift_heatmap, affine, post_process, out_avg, out_xy, out_maxval,
+      out_idx);
   PB_LAUNCH_CHECK("decode_flip_kernel");
   return PB200_OK;
 }

@@ -31,22 +31,29 @@ softargmax_fwd_kernel(const float* __restrict__ hm, long long maps, int H, int W
     float mx = -INFINITY;
     float z = 0.f, sx = 0.f, sy = 0.f;
     if (vec) {  // W % 4 == 0 and 16-byte aligned maps: a float4 never straddles a row
+      // ONE pass (online softmax): a running maximum per lane; the partial sums are rescaled
+      // whenever it grows, and once more when the lanes are merged
       const float4* b4 = reinterpret_cast<const float4*>(base);
       for (int i = lane; i < (HW >> 2); i += 32) {
         const float4 q = b4[i];
-        mx = fmaxf(mx, fmaxf(fmaxf(q.x * beta, q.y * beta), fmaxf(q.z * beta, q.w * beta)));
-      }
-      mx = warp_max(mx);
-      for (int i = lane; i < (HW >> 2); i += 32) {
-        const float4 q = b4[i];
+        const float v0 = q.x * beta, v1 = q.y * beta, v2 = q.z * beta, v3 = q.w * beta;
+        const float m4 = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+        if (m4 > mx) {
+          const float r = expf(mx - m4);   // 0 on the first chunk (mx = -inf)
+          z *= r; sx *= r; sy *= r;
+          mx = m4;
+        }
         const int e = 4 * i, y = e / W, x = e - y * W;
-        const float p0 = expf(q.x * beta - mx), p1 = expf(q.y * beta - mx), p2 = expf(q.z * beta - mx),
-                    p3 = expf(q.w * beta - mx);
+        const float p0 = expf(v0 - mx), p1 = expf(v1 - mx), p2 = expf(v2 - mx), p3 = expf(v3 - mx);
         const float ps = (p0 + p1) + (p2 + p3);
         z += ps;
         sx += ps * (float)x + (p1 + 2.f * p2 + 3.f * p3);
         sy = fmaf(ps, (float)y, sy);
       }
+      const float gm = warp_max(mx);
+      const float r = (mx == -INFINITY) ? 0.f : expf(mx - gm);   // lanes without elements contribute 0
+      z *= r; sx *= r; sy *= r;
+      mx = gm;
     } else {
       for (int e = lane; e < HW; e += 32) mx = fmaxf(mx, base[e] * beta);
       mx = warp_max(mx);

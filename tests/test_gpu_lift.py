@@ -86,6 +86,13 @@ def test_fused_front_ends_agree(variant):
             hm[3, 2, 5, 7] = np.nan
             hm[9, 0] = -1.0
             res = lift_heatmaps(hm, center, scale, cams, return_idx=True).numpy()
+            thr = lift_heatmaps(hm, center, scale, cams, conf_thre=1.5, return_proj=True).numpy()
+            few = (thr.maxvals.reshape(16, 4, 17) > 1.5).sum(axis=1) < 2          # joints with < 2 confident views
+            assert few.any() and not few.all()
+            assert np.all(thr.poses3d[few] == 0) and np.all(thr.reproj_err.reshape(16, 4, 17)[:, 0][few] == 0)
+            vis = np.nan_to_num(thr.maxvals, nan=-1.0) > 1.5
+            ref_thr = otri.triangulate_poses(cams, np.nan_to_num(thr.xy), vis)
+            assert np.abs(thr.poses3d - ref_thr)[~few].max() < 1e-2
             assert np.array_equal(res.idx, oinf.flat_argmax(hm)), (variant, hw)
             rp, rm = oinf.get_final_preds(True, hm, center, scale)
             assert np.array_equal(res.maxvals, rm[:, :, 0], equal_nan=True)
