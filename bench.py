@@ -2,7 +2,7 @@
 """bench.py -- multiview frames/s of the lifting hot path on N B200s (BASELINE.json).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload lift|rpsm|pseudo] [--frames B]
+                    [--workload lift|rpsm|pseudo] [--frames B] [--views V] [--joints J] [--hw S]
 
 A "step" is one pass of the hot path over one batch of synthetic input.  The default
 workload is BASELINE.json configs[1]: batched heatmap decode + DLT triangulation +
@@ -16,7 +16,8 @@ ONE JSON line is printed by rank 0:
                (pose_unsupervised_b200.multiviews.triangulate.lift_heatmaps), host->device
                copy of the heatmaps from pinned memory and device->host copy of the
                results inside the timed region
-  roofline     the dominant kernel (lift_fused_kernel) against the measured HBM peak
+  roofline     the dominant kernel (decode_tma_kernel, the only pass over the heatmaps) against the
+               measured HBM peak; `lift_path_ms` / `whole_path_frac` cover decode + lift together
   cpu_baseline the oracle port of the reference's CPU path timed on this box's host cores
                on a bounded sample of the same workload (rank 0, N=1 only)
 --impl reference times that CPU path alone (all host cores) and prints the same line shape.
@@ -437,12 +438,15 @@ def run_rpsm(args):
     from pose_unsupervised_b200.multiviews import pictorial
     from pose_unsupervised_b200.multiviews.body import HumanBody
     from pose_unsupervised_b200.utils import synth
-    from tests.util import rpsm_config
+    import types
     torch.cuda.set_device(0)
     B = args.frames if args.frames != 4096 else 296
     body = HumanBody.h36m17()
     edges = body.edges()
-    cfg = rpsm_config()
+    cfg = types.SimpleNamespace(
+        NETWORK=types.SimpleNamespace(IMAGE_SIZE=np.array([256, 256]), HEATMAP_SIZE=np.array([64, 64])),
+        PICT_STRUCT=types.SimpleNamespace(FIRST_NBINS=16, RECUR_NBINS=2, RECUR_DEPTH=10, GRID_SIZE=2000,
+                                          LIMB_LENGTH_TOLERANCE=150))
     base = 8
     poses = synth.random_poses(base, seed=1)
     avg = {e: float(np.mean([np.linalg.norm(p[e[0]] - p[e[1]]) for p in synth.random_poses(64, seed=99)]))
@@ -495,8 +499,7 @@ def run_pseudo(args):
     from pose_unsupervised_b200.multiviews.cameras import CameraTable, pack_camera
     from pose_unsupervised_b200.multiviews.triangulate import ransac, reproject_poses
     from pose_unsupervised_b200.utils import synth
-    from oracle import epipolar as oepi          # only to build the exact F table (input data)
-    from tests.util import pseudo_config
+    import types
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -523,11 +526,12 @@ def run_pseudo(args):
     obs[bad] += rng.normal(0, 50.0, (int(bad.sum()), 2))
     conf = rng.uniform(0.04, 1.12, obs.shape[:2]).astype(np.float32)
     table = CameraTable.from_arrays(pack, (subj[:, None] * 4 + np.arange(4)[None]).reshape(-1))
-    ftab = FundamentalTable(oepi.fundamental_table({s_: rigs[s_] for s_ in range(7)}), 4)
+    ftab = FundamentalTable.from_cameras({s_: rigs[s_] for s_ in range(7)})
     d_obs = rt.to_device(obs.astype(np.float32))
     d_conf = rt.to_device(conf)
     d_subj = torch.from_numpy(subj).to(dev)
-    cfg = pseudo_config(10.0, 3, False)
+    cfg = types.SimpleNamespace(DATASET=types.SimpleNamespace(NO_DISTORTION=False),
+                                PSEUDO_LABEL=types.SimpleNamespace(REPROJ_THRE=10.0, NUM_INLIERS=3))
     subj_list = subj
 
     def step():
