@@ -532,7 +532,7 @@ def run_pseudo(args):
     d_subj = torch.from_numpy(subj).to(dev)
     cfg = types.SimpleNamespace(DATASET=types.SimpleNamespace(NO_DISTORTION=False),
                                 PSEUDO_LABEL=types.SimpleNamespace(REPROJ_THRE=10.0, NUM_INLIERS=3))
-    subj_list = subj
+    subj_list = ftab.slots(subj)                                      # table slots, computed once
 
     def step():
         vis = d_conf > 0.7                                            # test_pseudo_label.py:194

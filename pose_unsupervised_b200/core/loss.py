@@ -63,8 +63,17 @@ class FundamentalTable(object):
                 for a in range(self.nviews) for b in range(self.nviews) if a != b}
 
     def slots(self, subjects):
-        subs = subjects.tolist() if hasattr(subjects, 'tolist') else list(subjects)
-        return rt.to_device(np.array([self.slot[s] for s in subs], dtype=np.int32))
+        """Subject ids [B] -> CUDA int32 table slots.  A CUDA int32 tensor is taken to hold slots
+        already (compute them once with this method when the same frames are scored repeatedly)."""
+        if isinstance(subjects, torch.Tensor) and subjects.is_cuda and subjects.dtype == torch.int32:
+            return subjects
+        subs = np.asarray(subjects.cpu() if isinstance(subjects, torch.Tensor) else subjects).reshape(-1)
+        keys = np.array(sorted(self.slot))
+        pos = np.searchsorted(keys, subs)
+        if np.any(pos >= len(keys)) or np.any(keys[np.minimum(pos, len(keys) - 1)] != subs):
+            raise KeyError('subject without fundamental matrices')
+        lut = np.array([self.slot[k] for k in keys.tolist()], dtype=np.int32)
+        return rt.to_device(lut[pos])
 
 
 def epipolar_residuals(pred2d, subjects, fundamental, nviews=4, weight=None, return_sum=False):
