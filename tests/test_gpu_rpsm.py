@@ -147,3 +147,53 @@ def test_rpsm_zero_and_negative_energies(pict):
                                      np.array([[limb[e] for e in edges]]), table, cfg, body, return_trace=True)
         assert np.array_equal(trace[0], rtrace)
         assert np.array_equal(got[0], ref)
+
+
+def _frame(body_edges, njoints, seed, nviews=4):
+    poses = synth.random_poses(1, seed=seed, njoints=njoints)[0]
+    cams = synth.camera_ring(nviews, seed=seed + 1)
+    boxes = synth.crop_box(cams, poses)
+    hm = synth.gaussian_heatmaps(cams, boxes, poses, 64, 256, 2.0, 0.02, seed=seed)
+    limb = synth.limb_lengths(poses, body_edges)
+    return poses, cams, boxes, hm, limb
+
+
+def test_rpsm_generic_grid_sizes_vs_oracle(pict):
+    """Non-default shapes take the generic code paths: 8^3 level-0 grid, 3^3 refinement grids
+    (27 bins per joint, no shuffle merge), 2 views, depth 3."""
+    from pose_unsupervised_b200.multiviews.body import HumanBody
+    body, obody = HumanBody(), OracleBody()
+    edges = obody.edges()
+    cfg = rpsm_config(first=8, recur=3, depth=3)
+    poses, cams, boxes, hm, limb = _frame(edges, 16, seed=71, nviews=2)
+    avg = {e: limb[e] * 1.05 for e in edges}
+    table = pict.PairwiseTable.from_limb_lengths(avg, body, 2000, 8)
+    opw = opict.level0_pairwise(2000, avg, 8, obody)
+    root = poses[6] + [15.0, -10.0, 5.0]
+    ref, rtrace = opict.rpsm(cams, hm, boxes, root, limb, opw, cfg, obody, return_trace=True)
+    got, trace = pict.rpsm_batch(cams, hm[None], np.array([b['center'] for b in boxes]),
+                                 np.array([b['scale'] for b in boxes]), root[None],
+                                 np.array([[limb[e] for e in edges]]), table, cfg, body, return_trace=True)
+    assert np.array_equal(trace[0], rtrace) and np.array_equal(got[0], ref)
+
+
+def test_rpsm_wide_shells_take_the_sorted_walk(pict):
+    """Limbs longer than 5 grid cells exceed the enumeration reach: the offset-table path then sorts
+    the child bins and walks to the first allowed one.  Same answer as the oracle."""
+    from pose_unsupervised_b200.multiviews.body import HumanBody
+    body, obody = HumanBody(), OracleBody()
+    edges = obody.edges()
+    cfg = rpsm_config(depth=2)
+    poses, cams, boxes, hm, limb = _frame(edges, 16, seed=81)
+    avg = {e: max(limb[e], 200.0) * 2.2 for e in edges}          # up to ~1000 mm: reach 7-10 cells of 133 mm
+    assert max(avg.values()) * 1.4 / (2000 / 15) > 5.5
+    table = pict.PairwiseTable.from_limb_lengths(avg, body, 2000, 16)
+    opw = opict.level0_pairwise(2000, avg, 16, obody)
+    root = poses[6]
+    ref, rtrace = opict.rpsm(cams, hm, boxes, root, limb, opw, cfg, obody, return_trace=True)
+    for use_lut in (True, False):
+        got, trace = pict.rpsm_batch(cams, hm[None], np.array([b['center'] for b in boxes]),
+                                     np.array([b['scale'] for b in boxes]), root[None],
+                                     np.array([[limb[e] for e in edges]]), table, cfg, body,
+                                     return_trace=True, use_lut=use_lut)
+        assert np.array_equal(trace[0], rtrace) and np.array_equal(got[0], ref), use_lut
