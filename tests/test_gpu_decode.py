@@ -147,3 +147,29 @@ def test_flip_test_fusion_matches_torch_recipe(inf, shift):
     assert torch.equal(avg, ref_rows)
     xy2, mv2, idx2 = inf.decode_heatmaps(ref_rows, center, scale, post_process=True, return_idx=True)
     assert torch.equal(idx, idx2) and torch.equal(mv, mv2) and torch.equal(xy, xy2)
+
+
+def test_ties_across_lanes_and_chunks(inf):
+    """Equal maxima planted at two positions of the map: the smaller flat index must win whichever
+    lanes, float4 slots or ring chunks the two positions fall into."""
+    rng = np.random.default_rng(11)
+    n, hw = 256, 64
+    hm = rng.random((n, 1, hw, hw), dtype=np.float32) * 0.5
+    flat = hm.reshape(n, -1)
+    special = [0, 1, 3, 4, 127, 128, 1023, 1024, 1025, 2047, 2048, 3071, 3072, 4094, 4095]
+    first = np.empty(n, dtype=np.int64)
+    for i in range(n):
+        a, b = (rng.choice(special, 2, replace=False) if i % 2 else rng.choice(hw * hw, 2, replace=False))
+        flat[i, a] = flat[i, b] = 0.75
+        if i % 5 == 0:                                  # a third, later copy
+            c = max(a, b) + (hw * hw - 1 - max(a, b)) // 2
+            flat[i, c] = 0.75
+        first[i] = min(a, b)
+    _, mv, idx = inf.decode_heatmaps(hm, return_idx=True)
+    assert np.array_equal(idx.cpu().numpy()[:, 0], first)
+    assert np.all(mv.cpu().numpy() == np.float32(0.75))
+    view = torch.from_numpy(hm).cuda()
+    buf = torch.empty(hm.size + 1, dtype=torch.float32, device='cuda')
+    buf[1:] = view.reshape(-1)
+    _, _, idx2 = inf.decode_heatmaps(buf[1:].view(n, 1, hw, hw), return_idx=True)   # unaligned: LDG path
+    assert np.array_equal(idx2.cpu().numpy()[:, 0], first)

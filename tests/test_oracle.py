@@ -203,3 +203,25 @@ def test_rpsm_matches_reference_golden():
         pose, trace = opict.rpsm(cams, hm, boxes, root, limb, pw, cfg, body, return_trace=True)
         assert np.array_equal(trace, r['f%d_trace' % f])
         assert np.array_equal(pose, r['f%d_pose' % f])
+
+
+def test_two_view_triangulation_matches_cv2_triangulatePoints():
+    """Independent anchor for the restated pymvg find3d: OpenCV's own linear (DLT + SVD) two-view
+    triangulation on the same projection matrices and the same (undistorted) observations."""
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(5)
+    rig = synth.camera_ring(4, seed=9)
+    poses = synth.random_poses(5, seed=10)
+    obs, cams = synth.multiview_observations(poses, [rig], [0] * 5, noise_px=1.5, seed=11, distorted=False)
+    system = otri.build_multi_camera_system([('camera_%d' % v, rig[v]) for v in range(4)], no_distortion=True)
+    worst = 0.0
+    for a, b in [(0, 1), (0, 3), (1, 2), (2, 3)]:
+        Pa, Pb = system._cams['camera_%d' % a].M, system._cams['camera_%d' % b].M
+        for f in range(5):
+            xa, xb = obs[f * 4 + a].T.copy(), obs[f * 4 + b].T.copy()          # [2, J]
+            Xh = cv2.triangulatePoints(Pa, Pb, xa, xb)                           # [4, J]
+            ref = (Xh[:3] / Xh[3]).T
+            for j in range(17):
+                got = system.find3d([('camera_%d' % a, obs[f * 4 + a, j]), ('camera_%d' % b, obs[f * 4 + b, j])])
+                worst = max(worst, np.linalg.norm(got - ref[j]))
+    assert worst < 1e-6                                                        # mm
