@@ -225,3 +225,45 @@ def test_two_view_triangulation_matches_cv2_triangulatePoints():
                 got = system.find3d([('camera_%d' % a, obs[f * 4 + a, j]), ('camera_%d' % b, obs[f * 4 + b, j])])
                 worst = max(worst, np.linalg.norm(got - ref[j]))
     assert worst < 1e-6                                                        # mm
+
+
+def test_affine_lu_emulation_vs_cv2_random():
+    """The elimination order restated in oracle.transforms reproduces cv2.getAffineTransform bit for bit
+    on thousands of random boxes (float32 and float64 inputs, with and without rotation)."""
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(123)
+    bad = 0
+    for i in range(1500):
+        c = rng.uniform(0, 1200, 2)
+        s = np.repeat(rng.uniform(0.2, 6.0), 2)
+        if i % 2:
+            c, s = c.astype(np.float32), s.astype(np.float32)
+        rot = 0.0 if i % 3 else rng.uniform(-90, 90)
+        size = [int(rng.choice([32, 48, 64, 80, 96, 256])), int(rng.choice([32, 48, 64, 80, 96, 256]))]
+        src, dst = otr.affine_point_triples(c, s, rot, size)
+        for frm, to in ((src, dst), (dst, src)):
+            ref = cv2.getAffineTransform(np.float32(frm), np.float32(to))
+            got = otr.solve_affine(frm, to)
+            bad += int(not np.array_equal(ref, got))
+    assert bad == 0
+
+
+def test_bilinear_restatement_vs_scipy_rgi_random():
+    """oracle.pictorial.bilinear_zero_outside against scipy's RegularGridInterpolator used exactly as
+    lib/multiviews/pictorial.py:176-187 uses it: interior, edges, outside, NaN -- bit for bit."""
+    interp = pytest.importorskip('scipy.interpolate')
+    rng = np.random.default_rng(7)
+    for h in (64, 17):
+        hmap = rng.random((h, h)).astype(np.float32)
+        xy = rng.uniform(-3, h + 2, (4000, 2))
+        xy[:50] = np.round(xy[:50])                               # exactly on grid lines
+        xy[50:60] = [h - 1, h - 1]
+        xy[60:70] = [0.0, h - 1]
+        xy[70:75] = [np.nextafter(h - 1.0, h), 3.0]               # just outside the upper edge
+        xy[75:80] = [-1e-12, 5.0]
+        xy[80:85] = [np.nan, 2.0]
+        rgi = interp.RegularGridInterpolator(points=[np.arange(h), np.arange(h)], values=hmap.transpose(),
+                                             bounds_error=False, fill_value=0)
+        ref = rgi(xy)
+        got = opict.bilinear_zero_outside(hmap, xy)
+        assert np.array_equal(ref, got, equal_nan=True)
