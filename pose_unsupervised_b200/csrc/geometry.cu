@@ -20,7 +20,7 @@ struct XYLoader {
   }
 };
 
-enum { kModeTriangulate = 0, kModeReproject = 1, kModeRansac = 2 };
+enum { kModeTriangulate = 0, kModeReproject = 1 };
 
 struct GeoParams {
   const double* campack;
@@ -59,12 +59,6 @@ __global__ void __launch_bounds__(128) geometry_kernel(GeoParams p) {
   }
   const bool nd = p.no_dist != 0;
 
-  if (kMode == kModeRansac) {
-    const uint32_t in = ransac_joint(p.campack, cam_row, V, nd, mask, xy, p.reproj_thre, p.num_inliers);
-    for (int v = 0; v < V; ++v) p.out_vis[(row0 + v) * J + j] = (in >> v) & 1u;
-    return;
-  }
-
   double X[3];
   const int nv = triangulate_joint(p.campack, cam_row, V, nd, mask, xy, X);
   if (p.out_X) {
@@ -82,6 +76,106 @@ __global__ void __launch_bounds__(128) geometry_kernel(GeoParams p) {
       if (p.out_err32) p.out_err32[o] = (float)e;
     }
   }
+}
+
+// ---- RANSAC with warp-level compaction of (joint, view pair) items -----------------------------
+// In geometry_kernel<., kModeRansac> every lane walks the pairs of its own joint, so a warp pays for
+// the joint with the most visible pairs (6 of 6 at V = 4) even when most joints have one or none -- the
+// normal case after the confidence threshold of run/test/test_pseudo_label.py:194.  Here the 32 joints
+// of a warp first list their (owner lane, view a, view b) items in shared memory (exclusive scan by
+// shuffles), then ALL lanes solve items 32 at a time, and finally every lane picks the winner among
+// its own items in itertools.combinations order with the reference's tie rules
+// (lib/multiviews/triangulate.py:140-165).  Same arithmetic per pair, same result, no idle lanes.
+struct PairItem {
+  uint8_t owner, a, b, pad;
+};
+struct PairResult {
+  double mean_err;
+  uint32_t in_mask;
+  int32_t count;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) ransac_compact_kernel(GeoParams p, int max_pairs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cap = 32 * max_pairs;
+  PairResult* res = reinterpret_cast<PairResult*>(smem_raw) + (size_t)warp * cap;
+  PairItem* items = reinterpret_cast<PairItem*>(smem_raw + (size_t)(blockDim.x >> 5) * cap * sizeof(PairResult)) +
+                    (size_t)warp * cap;
+  const int V = p.V, J = p.J;
+  const long long total = (long long)p.B * J;
+  const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane;  // first joint of this warp
+  const long long g = g0 + lane;
+  const bool valid = g < total;
+  uint32_t mask = 0u;
+  if (valid) {
+    const int f = (int)(g / J), j = (int)(g % J);
+    for (int v = 0; v < V; ++v)
+      if (p.vis == nullptr || p.vis[((size_t)f * V + v) * J + j]) mask |= 1u << v;
+  }
+  const int nvis = __popc(mask);
+  const int npairs = nvis * (nvis - 1) / 2;
+  // exclusive scan of npairs over the warp
+  int incl = npairs;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  const int base = incl - npairs;
+  const int n_items = __shfl_sync(0xffffffffu, incl, 31);
+  {
+    int k = base;
+    for (int a = 0; a < V; ++a) {
+      if (!((mask >> a) & 1u)) continue;
+      for (int b = a + 1; b < V; ++b) {
+        if (!((mask >> b) & 1u)) continue;
+        items[k++] = PairItem{(uint8_t)lane, (uint8_t)a, (uint8_t)b, 0};   // combinations order
+      }
+    }
+  }
+  __syncwarp();
+  const bool nd = p.no_dist != 0;
+  for (int it = lane; it < n_items; it += 32) {
+    const PairItem q = items[it];
+    const long long go = g0 + q.owner;
+    const int f = (int)(go / J), j = (int)(go % J);
+    const size_t row0 = (size_t)f * V;
+    const int32_t* cam_row = p.cam_index + row0;
+    XYLoader<T> xy{reinterpret_cast<const T*>(p.xy) + (row0 * J + j) * 2, J * 2};
+    double X[3];
+    triangulate_joint(p.campack, cam_row, V, nd, (1u << q.a) | (1u << q.b), xy, X);
+    uint32_t in_mask = 0u;
+    int count = 0;
+    double err_sum = 0.0;
+    for (int v = 0; v < V; ++v) {
+      double pu, pv;
+      const double e = reproject_view(p.campack, cam_row, v, nd, X, xy, pu, pv);
+      if (e < p.reproj_thre) { in_mask |= 1u << v; ++count; err_sum += e; }
+    }
+    PairResult r;
+    r.count = count;
+    r.in_mask = in_mask;
+    r.mean_err = count > 0 ? err_sum / (double)count : 0.0;
+    res[it] = r;
+  }
+  __syncwarp();
+  if (!valid) return;
+  uint32_t best_mask = 0u;
+  int best_count = 0;
+  double best_err = 10000.0;
+  for (int k = base; k < base + npairs; ++k) {
+    const PairResult r = res[k];
+    if (r.count < p.num_inliers) continue;
+    if (r.count > best_count || (r.count == best_count && r.mean_err < best_err)) {
+      best_mask = r.in_mask;
+      best_count = r.count;
+      best_err = r.mean_err;
+    }
+  }
+  const int f = (int)(g / J), j = (int)(g % J);
+  for (int v = 0; v < V; ++v) p.out_vis[((size_t)f * V + v) * J + j] = (best_mask >> v) & 1u;
 }
 
 __global__ void project_kernel(const double* __restrict__ campack, int cam_id,
@@ -254,7 +348,20 @@ extern "C" int pb200_ransac(const double* campack, const int32_t* cam_index, con
   PB_REQUIRE(num_inliers >= 1, "num_inliers must be >= 1 (the reference divides by it)");
   GeoParams p{campack, cam_index, xy, vis, B, V, J, no_distortion, reproj_thre, num_inliers,
               nullptr, nullptr, out_vis, nullptr, nullptr, 0, 0.f, nullptr};
-  return launch_geo<kModeRansac>(p, xy_dtype, stream);
+  const long long n = (long long)B * J;
+  if (n == 0) return PB200_OK;
+  const int max_pairs = V * (V - 1) / 2;
+  const size_t smem = (size_t)4 * 32 * max_pairs * (sizeof(pb200::PairResult) + sizeof(pb200::PairItem));
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  if (xy_dtype == PB200_F32) {
+    PB_CUDA(cudaFuncSetAttribute(pb200::ransac_compact_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pb200::ransac_compact_kernel<float><<<blocks, 128, smem, (cudaStream_t)stream>>>(p, max_pairs);
+  } else {
+    PB_CUDA(cudaFuncSetAttribute(pb200::ransac_compact_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pb200::ransac_compact_kernel<double><<<blocks, 128, smem, (cudaStream_t)stream>>>(p, max_pairs);
+  }
+  PB_LAUNCH_CHECK("ransac_compact_kernel");
+  return PB200_OK;
 }
 
 extern "C" int pb200_epipolar(const double* fmat, const int32_t* subj_index, const void* xy,
