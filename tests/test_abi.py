@@ -100,3 +100,13 @@ def test_frame_shard_covers_everything():
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     rows = np.arange(24).reshape(12, 2)
     assert np.array_equal(parallel.shard_rows(rows, 4, 1, 3), rows[4:8])
+
+
+def test_header_constants_match_binding():
+    text = open(HEADER).read()
+    consts = dict(re.findall(r'#define\s+(PB200_\w+)\s+\(?(-?\d+)\)?', text))
+    assert int(consts['PB200_MAX_VIEWS']) == _lib.MAX_VIEWS
+    assert int(consts['PB200_CAM_STRIDE']) == _lib.CAM_STRIDE
+    assert int(consts['PB200_RPSM_MAX_JOINTS']) == _lib.RPSM_MAX_JOINTS
+    assert (int(consts['PB200_F32']), int(consts['PB200_F64'])) == (_lib.F32, _lib.F64)
+    assert int(consts['PB200_OK']) == 0 and int(consts['PB200_ERR_ARG']) == -1

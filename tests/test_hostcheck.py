@@ -131,3 +131,25 @@ def test_two_view_pairs_vs_svd_oracle(hc):
                 hc.hc_triangulate(P(pk), P(xy), P(m), 4, 0, P(X))
                 worst = max(worst, np.linalg.norm(X - ref[j]))
     assert worst < 1e-5
+
+
+def test_plumb_bob_and_undistort_vs_oracle(hc):
+    """Device forward model (pymvg find2d) and the 5-iteration undistortion against the oracle's
+    restatement, including the no-distortion mode."""
+    rng = np.random.default_rng(3)
+    for seed in range(3):
+        cam = synth.camera_ring(4, seed=seed)[seed % 4]
+        rig = otri.build_multi_camera_system([('c', cam)], no_distortion=False)
+        rig_nd = otri.build_multi_camera_system([('c', cam)], no_distortion=True)
+        pk = pack_camera(cam)
+        pts = np.ascontiguousarray(rng.normal(0, 600, (50, 3)) + [0, 0, 900.0])
+        for model, system, distorted in ((1, rig, True), (2, rig_nd, True)):
+            out = np.zeros((50, 2))
+            hc.hc_project(P(pk), P(pts), 50, model, P(out))
+            ref = np.array([system.find2d('c', p, distorted=distorted) for p in pts])
+            assert np.abs(out - ref).max() < 1e-8
+        uv = np.ascontiguousarray(rng.uniform(100, 900, (50, 2)))
+        for nd, system in ((0, rig), (1, rig_nd)):
+            out = np.zeros((50, 2))
+            hc.hc_undistort(P(pk), nd, P(uv), 50, P(out))
+            assert np.abs(out - system._cams['c'].undistort(uv)).max() < 1e-9
