@@ -199,7 +199,7 @@ def run_reference_arm(args):
         'impl': 'reference', 'metric': metric_name(), 'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': warmup, 'ms_per_step': 1e3 * dt / steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 decode, f64 lift', 'data': 'synthetic',
-        'config': workload_config(cores * per_worker),
+        'config': dict(workload_config(args.frames), sample_frames_per_step=cores * per_worker),
         'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
