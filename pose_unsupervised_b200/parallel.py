@@ -7,7 +7,6 @@ the compute: an all-gather of the per-frame 3D poses and an all-reduce of the MP
 partial sums (run/test/test_triangulate.py:98-101), both issued on the compute
 stream.  The same code runs on CPU tensors with the gloo backend (tests).
 """
-import numpy as np
 import torch
 import torch.distributed as dist
 

@@ -1,13 +1,12 @@
 """Fused lift kernel against the two-kernel path (decode_tma_kernel + geometry_kernel) on the headline workload."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from bench import make_side_inputs
 from pose_unsupervised_b200 import runtime as rt
 from pose_unsupervised_b200.core.inference import decode_heatmaps
 from pose_unsupervised_b200.multiviews.cameras import CameraTable
 from pose_unsupervised_b200.multiviews.triangulate import lift_heatmaps, reproject_poses, triangulate_poses
-from pose_unsupervised_b200.utils.transforms import crop_affine
 
 B, V, J, HW = 4096, 4, 17, 64
 rigs, subj, pack, index, center, scale = make_side_inputs(B, 0)
