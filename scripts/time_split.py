@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import make_side_inputs
-from pose_unsupervised_b200 import runtime as rt
+from pose_unsupervised_b200 import _lib, runtime as rt
 from pose_unsupervised_b200.core.inference import decode_heatmaps
 from pose_unsupervised_b200.multiviews.cameras import CameraTable
 from pose_unsupervised_b200.multiviews.triangulate import lift_heatmaps, reproject_poses, triangulate_poses
@@ -29,7 +29,11 @@ def timeit(fn, n=100):
 
 
 def fused():
-    return lift_heatmaps(hm, dc, ds, table, return_proj=True)
+    _lib.call('pb200_set_tuning', 1, 1)          # one persistent kernel, TMA ring front end
+    try:
+        return lift_heatmaps(hm, dc, ds, table, return_proj=True)
+    finally:
+        _lib.call('pb200_set_tuning', 1, 2)      # default: two kernels
 
 
 def split():
