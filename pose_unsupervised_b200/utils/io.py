@@ -81,3 +81,51 @@ def pareto_select(acc, num):
         pending = [i for i in pending
                    if not (acc_order[i] <= acc_order[ref] and num_order[i] <= num_order[ref])]
     return keep
+
+
+def read_pairwise(path):
+    """data/testdata/pairwise_b16.pkl (run/test/generate_pairwise_constraints.py:109-111):
+    {'limb_length': {(p, c): mm}, 'pairwise_constrain': {(p, c): scipy sparse [n^3, n^3]}}."""
+    import pickle
+    with open(str(path), 'rb') as f:
+        d = pickle.load(f)
+    return d['limb_length'], d['pairwise_constrain']
+
+
+def write_rpsm_testdata(path, records):
+    """Write rows in the layout of run/test/generate_data_for_rpsm.py:110-117 (tests, examples)."""
+    import pickle
+    with open(str(path), 'wb') as f:
+        pickle.dump(list(records), f)
+    return str(path)
+
+
+def read_rpsm_testdata(path, body, nviews=4):
+    """data/testdata/rpsm_testdata_b16.pkl -> batched arrays for ``pictorial.rpsm_batch``.
+
+    The pickle is a list of per-(frame, view) dicts ``{'heatmap' [J,h,w], 'cam_params', 'joints_3d_cam'
+    [J,3], 'scale', 'center'}`` (run/test/generate_data_for_rpsm.py:110-117); grouping, ground truth,
+    grid centre (root joint of view 0 in world coordinates) and per-frame limb lengths follow
+    run/test/test_rpsm.py:81-126.  Returns a dict with ``cams`` (list of B*V camera dicts),
+    ``heatmaps [B,V,J,h,w]``, ``centers [B*V,2]``, ``scales [B*V,2]``, ``grid_centers [B,3]``,
+    ``limb_lengths [B,E]`` (``body.edges()`` order) and ``gt [B,J,3]``.
+    """
+    import pickle
+    with open(str(path), 'rb') as f:
+        db = pickle.load(f)
+    assert len(db) % nviews == 0
+    edges = body.edges()
+    cams, hms, centers, scales, roots, limbs, gts = [], [], [], [], [], [], []
+    for i in range(0, len(db), nviews):
+        group = db[i:i + nviews]
+        hms.append(np.array([g['heatmap'] for g in group], dtype=np.float32))
+        cams += [g['cam_params'] for g in group]
+        centers += [np.asarray(g['center'], dtype=np.float64).reshape(2) for g in group]
+        scales += [np.asarray(g['scale'], dtype=np.float64).reshape(-1)[:2] for g in group]
+        c0 = group[0]['cam_params']
+        pose = (np.asarray(c0['R']).T.dot(np.asarray(group[0]['joints_3d_cam']).T) + np.asarray(c0['T']).reshape(3, 1)).T
+        gts.append(pose)                                             # camera_to_world_frame of view 0
+        roots.append(pose[body.root_idx])
+        limbs.append([np.linalg.norm(pose[p] - pose[c]) for p, c in edges])
+    return {'cams': cams, 'heatmaps': np.array(hms), 'centers': np.array(centers), 'scales': np.array(scales),
+            'grid_centers': np.array(roots), 'limb_lengths': np.array(limbs), 'gt': np.array(gts)}

@@ -49,3 +49,27 @@ def test_pareto_selection():
     for _ in range(20):
         a, n = rng.random(9).round(2), rng.random(9).round(2)
         assert io.pareto_select(a, n) == _pareto_reference(a, n)
+
+
+def test_rpsm_testdata_round_trip(tmp_path):
+    """Rows in the reference's rpsm pickle layout -> batched arrays (run/test/test_rpsm.py:81-126)."""
+    from pose_unsupervised_b200.multiviews.body import HumanBody
+    from pose_unsupervised_b200.utils import synth
+    body = HumanBody()
+    poses = synth.random_poses(3, seed=1, njoints=16)
+    records = []
+    for f in range(3):
+        cams = synth.camera_ring(4, seed=f)
+        boxes = synth.crop_box(cams, poses[f])
+        hm = synth.gaussian_heatmaps(cams, boxes, poses[f], 16, 256, 1.0, 0.0, seed=f)
+        for v in range(4):
+            cam_xyz = (cams[v]['R'] @ (poses[f].T - cams[v]['T'])).T
+            records.append({'heatmap': hm[v], 'cam_params': cams[v], 'joints_3d_cam': cam_xyz,
+                            'scale': boxes[v]['scale'], 'center': boxes[v]['center']})
+    path = io.write_rpsm_testdata(tmp_path / 'rpsm_testdata_b16.pkl', records)
+    d = io.read_rpsm_testdata(path, body)
+    assert d['heatmaps'].shape == (3, 4, 16, 16, 16) and len(d['cams']) == 12
+    assert np.abs(d['gt'] - poses).max() < 1e-9
+    assert np.abs(d['grid_centers'] - poses[:, body.root_idx]).max() < 1e-9
+    e0 = body.edges()[0]
+    assert abs(d['limb_lengths'][1, 0] - np.linalg.norm(poses[1, e0[0]] - poses[1, e0[1]])) < 1e-9
