@@ -17,6 +17,21 @@ from .body import HumanBody
 from .cameras import CameraTable
 
 
+def pack_pairwise_bits(m):
+    """Dense 0/1 matrix [n, n] -> uint32 [n, ceil(n/32)]: bit (j % 32) of word [i, j // 32] is P[i, j]
+    (the layout pb200_rpsm reads; host-side packing of the reference's scipy matrices)."""
+    m = np.asarray(m)
+    nb = m.shape[0]
+    if m.shape != (nb, nb):
+        raise ValueError('pairwise matrix must be square')
+    if not np.all((m == 0) | (m == 1)):
+        raise ValueError('pairwise matrix must hold only 0/1 (generate_pairwise_constraints.py:93)')
+    words = (nb + 31) // 32
+    padded = np.zeros((nb, words * 32), dtype=np.uint8)
+    padded[:, :nb] = m != 0
+    return np.packbits(padded, axis=1, bitorder='little').view('<u4').astype(np.uint32)
+
+
 class PairwiseTable(object):
     """Level-0 pairwise constraints as bits: [E, nbins, ceil(nbins/32)] uint32 on the device."""
 
@@ -54,16 +69,8 @@ class PairwiseTable(object):
         for e in body.edges():
             m = pairwise[e]
             m = m.toarray() if hasattr(m, 'toarray') else np.asarray(m)
-            nb = m.shape[0]
-            if m.shape != (nb, nb):
-                raise ValueError('pairwise[%s] must be square' % (e,))
-            if not np.all((m == 0) | (m == 1)):
-                raise ValueError('pairwise[%s] must hold only 0/1 (generate_pairwise_constraints.py:93)' % (e,))
-            words = (nb + 31) // 32
-            padded = np.zeros((nb, words * 32), dtype=np.uint8)
-            padded[:, :nb] = m != 0
-            rows.append(np.packbits(padded, axis=1, bitorder='little').view('<u4'))
-        host = np.stack(rows).astype(np.uint32)
+            rows.append(pack_pairwise_bits(m))
+        host = np.stack(rows)
         table = cls(rt.to_device(host.view(np.int32)), host.shape[1])
         if len(cls._cache) > 4:
             cls._cache.clear()

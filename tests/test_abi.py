@@ -110,3 +110,18 @@ def test_header_constants_match_binding():
     assert int(consts['PB200_RPSM_MAX_JOINTS']) == _lib.RPSM_MAX_JOINTS
     assert (int(consts['PB200_F32']), int(consts['PB200_F64'])) == (_lib.F32, _lib.F64)
     assert int(consts['PB200_OK']) == 0 and int(consts['PB200_ERR_ARG']) == -1
+
+
+def test_pairwise_bit_packing_layout():
+    from pose_unsupervised_b200.multiviews.pictorial import pack_pairwise_bits
+    rng = np.random.default_rng(0)
+    for n in (27, 64, 100):
+        m = (rng.random((n, n)) < 0.3).astype(np.int8)
+        w = pack_pairwise_bits(m)
+        assert w.dtype == np.uint32 and w.shape == (n, (n + 31) // 32)
+        for i, j in rng.integers(0, n, (200, 2)):
+            assert ((int(w[i, j // 32]) >> (j % 32)) & 1) == m[i, j]
+    with pytest.raises(ValueError):
+        pack_pairwise_bits(np.full((4, 4), 2))
+    with pytest.raises(ValueError):
+        pack_pairwise_bits(np.zeros((4, 5)))
