@@ -212,6 +212,9 @@ int pb200_mpjpe_stats(const double* pred, const double* gt, int B, int J, double
  *   outputs   : out_xy/out_maxval/out_idx as pb200_decode; out_X [B,J,3] float64;
  *               out_err [B*V,J] float32 reprojection error in pixels (zeros where the joint
  *               was not lifted); out_proj [B*V,J,2] float64 or NULL.
+ *   epipolar  : with fmat [S,V,V,9] and subj_index [B] (as pb200_epipolar) and out_resid
+ *               [B, V(V-1), J] float64 non-NULL, the algebraic epipolar residuals of the decoded
+ *               coordinates are written in the same pass (all three NULL to skip).
  */
 size_t pb200_lift_workspace_bytes(int B, int V, int J);
 int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, int B, int V, int J, int H, int W,
@@ -220,6 +223,7 @@ int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, int B, int V,
                      int use_conf, float conf_thre,
                      float* out_xy, float* out_maxval, int32_t* out_idx,
                      double* out_X, float* out_err, double* out_proj,
+                     const double* fmat, const int32_t* subj_index, double* out_resid,
                      void* workspace, void* stream);
 
 /* Tuning hook (process-wide).  PB200_TUNE_LIFT_VARIANT selects how pb200_lift_fused runs:

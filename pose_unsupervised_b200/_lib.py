@@ -55,6 +55,7 @@ _PROTOS = {
     'pb200_lift_fused': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                  c_void_p, c_void_p, c_int, c_int, c_float,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
     'pb200_rpsm_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'pb200_rpsm': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

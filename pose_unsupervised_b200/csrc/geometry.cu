@@ -40,6 +40,10 @@ struct GeoParams {
   int use_conf;
   float conf_thre;
   float* out_err32;
+  // optional epipolar residuals of the same coordinates, [B, V(V-1), J]
+  const double* fmat;
+  const int32_t* subj;
+  double* out_resid;
 };
 
 template <typename T, int kMode>
@@ -75,6 +79,9 @@ __global__ void __launch_bounds__(128) geometry_kernel(GeoParams p) {
       if (p.out_err) p.out_err[o] = e;
       if (p.out_err32) p.out_err32[o] = (float)e;
     }
+    if (p.out_resid)
+      epipolar_joint(p.fmat + (size_t)p.subj[f] * V * V * 9, V, xy,
+                     p.out_resid + (size_t)f * V * (V - 1) * J + j, (size_t)J);
   }
 }
 
@@ -295,9 +302,10 @@ static int launch_geo(const GeoParams& p, int xy_dtype, void* stream) {
 // reproject the float32 coordinates the decode kernel just wrote.
 int launch_lift_after_decode(const double* campack, const int32_t* cam_index, const float* xy,
                              const float* maxval, int use_conf, float conf_thre, int B, int V, int J,
-                             int no_dist, double* out_X, float* out_err32, double* out_proj, void* stream) {
+                             int no_dist, double* out_X, float* out_err32, double* out_proj,
+                             const double* fmat, const int32_t* subj, double* out_resid, void* stream) {
   GeoParams p{campack, cam_index, xy, nullptr, B, V, J, no_dist, 0.0, 0, out_X, out_proj, nullptr, nullptr,
-              maxval, use_conf, conf_thre, out_err32};
+              maxval, use_conf, conf_thre, out_err32, fmat, subj, out_resid};
   return launch_geo<kModeReproject>(p, PB200_F32, stream);
 }
 
@@ -323,7 +331,7 @@ extern "C" int pb200_triangulate(const double* campack, const int32_t* cam_index
   if (rc != PB200_OK) return rc;
   PB_REQUIRE(out_X, "out_X is null");
   GeoParams p{campack, cam_index, xy, vis, B, V, J, no_distortion, 0.0, 0, out_X, nullptr, nullptr, nullptr,
-              nullptr, 0, 0.f, nullptr};
+              nullptr, 0, 0.f, nullptr, nullptr, nullptr, nullptr};
   return launch_geo<kModeTriangulate>(p, xy_dtype, stream);
 }
 
@@ -335,7 +343,7 @@ extern "C" int pb200_reproject(const double* campack, const int32_t* cam_index, 
   if (rc != PB200_OK) return rc;
   PB_REQUIRE(out_proj && out_vis, "out_proj / out_vis is null");
   GeoParams p{campack, cam_index, xy, vis, B, V, J, no_distortion, 0.0, 0, out_X, out_proj, out_vis, out_err,
-              nullptr, 0, 0.f, nullptr};
+              nullptr, 0, 0.f, nullptr, nullptr, nullptr, nullptr};
   return launch_geo<kModeReproject>(p, xy_dtype, stream);
 }
 
@@ -347,7 +355,7 @@ extern "C" int pb200_ransac(const double* campack, const int32_t* cam_index, con
   PB_REQUIRE(out_vis, "out_vis is null");
   PB_REQUIRE(num_inliers >= 1, "num_inliers must be >= 1 (the reference divides by it)");
   GeoParams p{campack, cam_index, xy, vis, B, V, J, no_distortion, reproj_thre, num_inliers,
-              nullptr, nullptr, out_vis, nullptr, nullptr, 0, 0.f, nullptr};
+              nullptr, nullptr, out_vis, nullptr, nullptr, 0, 0.f, nullptr, nullptr, nullptr, nullptr};
   const long long n = (long long)B * J;
   if (n == 0) return PB200_OK;
   const int max_pairs = V * (V - 1) / 2;

@@ -54,5 +54,29 @@ __device__ __forceinline__ double reproject_view(const double* __restrict__ camp
   return sqrt(dx * dx + dy * dy);
 }
 
+// Algebraic epipolar residuals |x_b^T F_(a,b) x_a| of one joint for the V(V-1) ordered view pairs
+// (itertools.permutations order), lib/core/loss.py:121-127, run/test/test_fund_mtx.py:61-67.
+// fmat_subj: the [V][V][9] block of the frame's subject; out[pr * pair_stride] receives pair pr.
+template <typename XYFn>
+__device__ __forceinline__ void epipolar_joint(const double* __restrict__ fmat_subj, int V, XYFn xy,
+                                               double* __restrict__ out, size_t pair_stride) {
+  int pr = 0;
+  for (int a = 0; a < V; ++a) {
+    double xa, ya;
+    xy(a, xa, ya);
+    for (int b = 0; b < V; ++b) {
+      if (b == a) continue;
+      double xb, yb;
+      xy(b, xb, yb);
+      const double* F = fmat_subj + ((size_t)a * V + b) * 9;
+      const double t0 = fma(yb, F[3], xb * F[0]) + F[6];
+      const double t1 = fma(yb, F[4], xb * F[1]) + F[7];
+      const double t2 = fma(yb, F[5], xb * F[2]) + F[8];
+      out[(size_t)pr * pair_stride] = fabs((t0 * xa + t1 * ya) + t2);
+      ++pr;
+    }
+  }
+}
+
 }  // namespace pb200
 #endif

@@ -65,6 +65,9 @@ struct FusedParams {
   double* out_X;
   float* out_err;
   double* out_proj;
+  const double* fmat;     // optional epipolar table [S][V][V][9], subject slot per frame, residuals out
+  const int32_t* subj;
+  double* out_resid;
   int32_t* ws;     // [0] next map, [1] finished blocks, [4 + f] maps decoded of frame f
   float4* records; // [B*V*J] {x, y, maxval, tag}
 };
@@ -107,6 +110,9 @@ __device__ __noinline__ void lift_frame_joint(const FusedParams& p, int f, int j
     p.out_err[o] = (float)e;
     if (p.out_proj) { p.out_proj[2 * o] = pu; p.out_proj[2 * o + 1] = pv; }
   }
+  if (p.out_resid)
+    epipolar_joint(p.fmat + (size_t)p.subj[f] * V * V * 9, V, xy,
+                   p.out_resid + (size_t)f * V * (V - 1) * J + j, (size_t)J);
   for (int v = 0; v < V; ++v)  // leave the workspace clean for the next launch
     p.records[(row0 + v) * J + j] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
@@ -214,7 +220,8 @@ int launch_decode(const HmViews& hv, int N, int J, int H, int W, const double* a
                   float* out_xy, float* out_maxval, int32_t* out_idx, void* stream);
 int launch_lift_after_decode(const double* campack, const int32_t* cam_index, const float* xy,
                              const float* maxval, int use_conf, float conf_thre, int B, int V, int J,
-                             int no_dist, double* out_X, float* out_err32, double* out_proj, void* stream);
+                             int no_dist, double* out_X, float* out_err32, double* out_proj,
+                             const double* fmat, const int32_t* subj, double* out_resid, void* stream);
 
 // 2 = two kernels (decode, then one thread per (frame, joint)); measured faster than either fused
 // kernel on B200 because lifting inside the streaming warps steals their time (profiles/)
@@ -242,6 +249,7 @@ extern "C" int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, in
                                 const double* campack, const int32_t* cam_index, int no_distortion,
                                 int use_conf, float conf_thre, float* out_xy, float* out_maxval,
                                 int32_t* out_idx, double* out_X, float* out_err, double* out_proj,
+                                const double* fmat, const int32_t* subj_index, double* out_resid,
                                 void* workspace, void* stream) {
   PB_REQUIRE(B >= 0 && J >= 1 && H >= 1 && W >= 1, "bad shape B=%d J=%d H=%d W=%d", B, J, H, W);
   if (B == 0) return PB200_OK;
@@ -252,6 +260,7 @@ extern "C" int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, in
   PB_REQUIRE(out_xy && out_maxval && out_X && out_err && workspace, "null output / workspace pointer");
   PB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "workspace must be 16-byte aligned");
   PB_REQUIRE(n_ptr == 1 || n_ptr == V, "n_ptr must be 1 or V");
+  PB_REQUIRE(out_resid == nullptr || (fmat && subj_index), "out_resid needs fmat and subj_index");
   FusedParams p;
   int rc = fill_views(hm_views_host, n_ptr, B * V, p.hv);
   if (rc != PB200_OK) return rc;
@@ -262,6 +271,7 @@ extern "C" int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, in
   p.use_conf = use_conf; p.conf_thre = conf_thre;
   p.out_xy = out_xy; p.out_maxval = out_maxval; p.out_idx = out_idx;
   p.out_X = out_X; p.out_err = out_err; p.out_proj = out_proj;
+  p.fmat = fmat; p.subj = subj_index; p.out_resid = out_resid;
   p.ws = reinterpret_cast<int32_t*>(workspace);
   const size_t ints = (((size_t)B + 4 + 3) / 4) * 4;
   p.records = reinterpret_cast<float4*>(p.ws + ints);
@@ -269,7 +279,8 @@ extern "C" int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, in
     rc = launch_decode(p.hv, B * V, J, H, W, affine, post_process, out_xy, out_maxval, out_idx, stream);
     if (rc != PB200_OK) return rc;
     return launch_lift_after_decode(campack, cam_index, out_xy, out_maxval, use_conf, conf_thre, B, V, J,
-                                    no_distortion, out_X, out_err, out_proj, stream);
+                                    no_distortion, out_X, out_err, out_proj, fmat, subj_index, out_resid,
+                                    stream);
   }
   const int sm = cached_sm_count();
   if (sm <= 0) return PB200_ERR_CUDA;

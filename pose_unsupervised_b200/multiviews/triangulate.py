@@ -82,19 +82,20 @@ def reproject_poses(poses2d, camera_params, joints_vis, no_distortion=False, nvi
 class LiftResult(object):
     """Outputs of :func:`lift_heatmaps` (CUDA tensors; ``.numpy()`` copies them to the host)."""
 
-    def __init__(self, xy, maxvals, idx, poses3d, reproj_err, proj2d):
+    def __init__(self, xy, maxvals, idx, poses3d, reproj_err, proj2d, epipolar=None):
         self.xy, self.maxvals, self.idx = xy, maxvals, idx
         self.poses3d, self.reproj_err, self.proj2d = poses3d, reproj_err, proj2d
+        self.epipolar = epipolar          # [B, V(V-1), J] float64 or None
 
     def numpy(self):
         f = lambda t: None if t is None else t.cpu().numpy()
         return LiftResult(f(self.xy), f(self.maxvals), f(self.idx), f(self.poses3d),
-                          f(self.reproj_err), f(self.proj2d))
+                          f(self.reproj_err), f(self.proj2d), f(self.epipolar))
 
 
 def lift_heatmaps(heatmaps, center, scale, camera_params, nviews=4, post_process=True,
                   no_distortion=False, conf_thre=None, return_idx=False, return_proj=False,
-                  affine=None, out_poses3d=None):
+                  affine=None, out_poses3d=None, fundamental=None, subjects=None):
     """Heatmaps -> 2D joints -> 3D poses -> reprojection error in one pass over HBM.
 
     Equivalent to ``get_final_preds`` (lib/core/inference.py:50-75) on every row followed by
@@ -104,7 +105,9 @@ def lift_heatmaps(heatmaps, center, scale, camera_params, nviews=4, post_process
     per-view tensors [B,J,H,W].  ``affine`` may carry the [N,2,3] result of
     ``crop_affine(center, scale, (W, H), inv=1)`` when the caller already has it;
     ``out_poses3d`` a preallocated CUDA float64 [B,J,3] tensor to write the poses into (e.g. the
-    send buffer of ``parallel.PoseExchange``).
+    send buffer of ``parallel.PoseExchange``).  With ``fundamental`` (a ``core.loss.FundamentalTable``)
+    and ``subjects`` [B], the algebraic epipolar residuals of the decoded coordinates
+    (run/test/test_fund_mtx.py:56-69) are produced in the same pass as ``result.epipolar``.
     """
     rt.require_device()
     views, N, J, H, W = _view_pointers(heatmaps)
@@ -132,6 +135,14 @@ def lift_heatmaps(heatmaps, center, scale, camera_params, nviews=4, post_process
             raise ValueError('out_poses3d must be a contiguous CUDA float64 [%d, %d, 3] tensor' % (B, J))
     err = rt.empty((N, J), torch.float32)
     proj = rt.empty((N, J, 2), torch.float64) if return_proj else None
+    fmat = slots = resid = None
+    if fundamental is not None:
+        if subjects is None:
+            raise ValueError('subjects [B] are needed with a fundamental table')
+        fmat, slots = fundamental.fmat, fundamental.slots(subjects)
+        if int(slots.shape[0]) != B or fundamental.nviews != nviews:
+            raise ValueError('fundamental table / subjects do not match the batch')
+        resid = rt.empty((B, nviews * (nviews - 1), J), torch.float64)
     ws = rt.workspace('lift', _lib.load().pb200_lift_workspace_bytes(B, nviews, J))
     ptrs = (ctypes.c_void_p * len(views))(*[v.data_ptr() for v in views])
     _lib.call('pb200_lift_fused', ptrs, len(views), B, nviews, J, H, W, rt.ptr(affine),
@@ -139,8 +150,8 @@ def lift_heatmaps(heatmaps, center, scale, camera_params, nviews=4, post_process
               int(bool(no_distortion)), int(conf_thre is not None),
               float(0.0 if conf_thre is None else conf_thre),
               rt.ptr(xy), rt.ptr(maxvals), rt.ptr(idx), rt.ptr(poses3d), rt.ptr(err), rt.ptr(proj),
-              rt.ptr(ws), rt.stream_ptr())
-    return LiftResult(xy, maxvals, idx, poses3d, err, proj)
+              rt.ptr(fmat), rt.ptr(slots), rt.ptr(resid), rt.ptr(ws), rt.stream_ptr())
+    return LiftResult(xy, maxvals, idx, poses3d, err, proj, resid)
 
 
 def mpjpe_stats(pred3d, gt3d, out=None):

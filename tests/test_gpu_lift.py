@@ -150,3 +150,32 @@ def test_fused_full_size_properties():
     # random heatmaps give inconsistent views: the DLT solution is far away and ill-conditioned,
     # so compare relative to the magnitude of the point
     assert (np.abs(got - ref) / np.maximum(1.0, np.abs(ref))).max() < 1e-6
+
+
+@pytest.mark.parametrize('variant', [1, 2])
+def test_lift_with_epipolar_residuals_in_the_same_pass(variant):
+    """north_star: reprojection error and epipolar residuals come out of the same pass.  They must equal
+    the stand-alone epipolar kernel on the decoded coordinates, and the oracle."""
+    from oracle import epipolar as oepi
+    from pose_unsupervised_b200 import _lib
+    from pose_unsupervised_b200.core.loss import FundamentalTable, epipolar_residuals
+    from pose_unsupervised_b200.multiviews.triangulate import lift_heatmaps
+    B, V, J = 12, 4, 17
+    rng = np.random.default_rng(3)
+    rigs = synth.camera_table(3, V, seed=3)
+    subj = rng.integers(0, 3, B)
+    cams = [rigs[s][v] for s in subj for v in range(V)]
+    hm = rng.random((B * V, J, 64, 64), dtype=np.float32)
+    center = rng.uniform(400, 600, (B * V, 2))
+    scale = np.repeat(rng.uniform(1.5, 3.0, (B * V, 1)), 2, axis=1)
+    table = FundamentalTable.from_cameras({s: rigs[s] for s in range(3)})
+    _lib.call('pb200_set_tuning', 1, variant)
+    try:
+        res = lift_heatmaps(hm, center, scale, cams, fundamental=table, subjects=subj)
+    finally:
+        _lib.call('pb200_set_tuning', 1, 2)
+    alone = epipolar_residuals(res.xy, subj, table)
+    assert res.epipolar.shape == (B, V * (V - 1), J) and torch.equal(res.epipolar, alone)
+    F = oepi.fundamental_table({s: rigs[s] for s in range(3)})
+    ref = oepi.epipolar_residuals(res.xy.cpu().numpy().astype(np.float64), subj, F)
+    assert np.abs(res.epipolar.cpu().numpy() - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max())
