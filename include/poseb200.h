@@ -57,13 +57,18 @@ int pb200_device_check(void);
 int pb200_sm_count(void);
 
 /* ---- crop affine ----------------------------------------------------------------
- * Replaces utils.transforms.get_affine_transform(center, scale, rot=0, output_size,
+ * Replaces utils.transforms.get_affine_transform(center, scale, rot, output_size, shift,
  * inv) (lib/utils/transforms.py:76-109), one 2x3 float64 matrix per row, following
- * cv2.getAffineTransform's float32 staging and elimination order bit for bit.
+ * numpy's dtype promotion of the float32 point triples and cv2.getAffineTransform's
+ * elimination order bit for bit.
  *   center [n,2], scale [n,2] : dtype given by center_dtype / scale_dtype
+ *   rot_sincos [n,2] float64  : (np.sin, np.cos) of np.pi * rot / 180 per row, evaluated by
+ *                               the caller on the host; NULL = no rotation (the lifting path)
+ *   shift_x, shift_y          : the `shift` argument (default 0, 0) and its dtype tag
  *   out    [n,6] float64 row-major 2x3
  */
 int pb200_crop_affine(const void* center, int center_dtype, const void* scale, int scale_dtype,
+                      const double* rot_sincos, double shift_x, double shift_y, int shift_dtype,
                       int n, int out_w, int out_h, int inv, double* out, void* stream);
 
 /* ---- heatmap decode ---------------------------------------------------------------
@@ -106,7 +111,8 @@ int pb200_transform_preds(const void* coords, int coords_dtype, const double* af
  * model 0 replaces multiviews.cameras.project_pose (lib/multiviews/cameras.py:25-54,
  * averaged focal length, H36M tangential form); model 1 is pymvg find2d
  * (distorted plumb-bob, lib/multiviews/triangulate.py:147,210); model 2 is model 1
- * without distortion.  pts [n,3] float64 world -> out [n,2] float64 pixels.
+ * without distortion; model 3 is model 0 with separate fx, fy (project_point_radial with
+ * f = [fx, fy], cameras.py:17-18,52).  pts [n,3] float64 world -> out [n,2] float64 pixels.
  */
 int pb200_project(const double* campack, int cam_id, const double* pts, int n, int model,
                   double* out, void* stream);
@@ -200,23 +206,20 @@ int pb200_epipolar_grad(const double* fmat, const int32_t* subj_index, const voi
 int pb200_mpjpe_stats(const double* pred, const double* gt, int B, int J, double* out4,
                       void* stream);
 
-/* ---- fused lift: decode -> triangulate -> reprojection error, one pass over HBM ----
- * The headline path of BASELINE.json (config 2): pb200_decode (get_final_preds)
- * followed by pb200_reproject on the decoded coordinates, in one persistent kernel;
- * the warp that finishes the last map of a frame lifts that frame.
+/* ---- lift: decode -> triangulate -> reprojection error (+ epipolar residuals) --------
+ * The headline path of BASELINE.json (config 2): pb200_decode (get_final_preds) followed
+ * by pb200_reproject on the decoded coordinates with joints_vis = maxval > conf_thre, issued
+ * back to back on `stream`.  The heatmaps are read from HBM exactly once; the lift reads the
+ * decoded coordinates back from L2.
  *   conf_thre : a joint is visible in a view iff maxval > conf_thre
  *               (run/test/test_pseudo_label.py:194); pass use_conf = 0 for "all visible"
- *   workspace : pb200_lift_workspace_bytes(B, V, J) bytes, 16-byte aligned, zero-initialised
- *               once by the caller; the kernel leaves it all-zero (arrival counters and the
- *               16-byte hand-off records, see csrc/lift_fused.cu).
  *   outputs   : out_xy/out_maxval/out_idx as pb200_decode; out_X [B,J,3] float64;
  *               out_err [B*V,J] float32 reprojection error in pixels (zeros where the joint
  *               was not lifted); out_proj [B*V,J,2] float64 or NULL.
  *   epipolar  : with fmat [S,V,V,9] and subj_index [B] (as pb200_epipolar) and out_resid
  *               [B, V(V-1), J] float64 non-NULL, the algebraic epipolar residuals of the decoded
- *               coordinates are written in the same pass (all three NULL to skip).
+ *               coordinates are written by the same lift threads (all three NULL to skip).
  */
-size_t pb200_lift_workspace_bytes(int B, int V, int J);
 int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, int B, int V, int J, int H, int W,
                      const double* affine, int post_process,
                      const double* campack, const int32_t* cam_index, int no_distortion,
@@ -224,14 +227,7 @@ int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, int B, int V,
                      float* out_xy, float* out_maxval, int32_t* out_idx,
                      double* out_X, float* out_err, double* out_proj,
                      const double* fmat, const int32_t* subj_index, double* out_resid,
-                     void* workspace, void* stream);
-
-/* Tuning hook (process-wide).  PB200_TUNE_LIFT_VARIANT selects how pb200_lift_fused runs:
- * 0 = one fused kernel, LDG.128 front end; 1 = one fused kernel, per-warp TMA bulk-copy ring;
- * 2 = two kernels back to back (TMA decode, then one thread per (frame, joint)) -- the default,
- * fastest on B200.  All three give identical results. */
-#define PB200_TUNE_LIFT_VARIANT 1
-int pb200_set_tuning(int key, int value);
+                     void* stream);
 
 /* ---- RPSM: recursive pictorial structure grid search -------------------------------
  * Replaces multiviews.pictorial.rpsm (lib/multiviews/pictorial.py:214-250) for a

@@ -25,8 +25,8 @@ _PROTOS = {
     'pb200_last_error': (c_char_p, []),
     'pb200_device_check': (c_int, []),
     'pb200_sm_count': (c_int, []),
-    'pb200_crop_affine': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                  c_void_p, c_void_p]),
+    'pb200_crop_affine': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_double, c_double, c_int,
+                                  c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'pb200_decode': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
     'pb200_decode_flip': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
@@ -50,13 +50,11 @@ _PROTOS = {
     'pb200_epipolar_grad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                     c_double, c_void_p, c_void_p]),
     'pb200_mpjpe_stats': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    'pb200_lift_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
-    'pb200_set_tuning': (c_int, [c_int, c_int]),
     'pb200_lift_fused': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                  c_void_p, c_void_p, c_int, c_int, c_float,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_void_p]),
+                                 c_void_p]),
     'pb200_rpsm_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'pb200_rpsm': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                            c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,

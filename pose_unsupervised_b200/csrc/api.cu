@@ -15,18 +15,29 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int cached_sm_count() {
-  static int sm = 0;
-  if (sm > 0) return sm;
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
-  if (e != cudaSuccess) {
-    set_error("no usable CUDA device: %s", cudaGetErrorString(e));
-    sm = 0;
+int current_device_ordinal() {
+  int dev = -1;
+  const cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+    set_error("no usable CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range");
     return -1;
   }
-  return sm;
+  return dev;
+}
+
+int cached_sm_count() {
+  static int sm[kMaxDevices] = {0};   // one slot per device ordinal: a process may drive several GPUs
+  const int dev = current_device_ordinal();
+  if (dev < 0) return -1;
+  if (sm[dev] > 0) return sm[dev];
+  int n = 0;
+  const cudaError_t e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("no usable CUDA device: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  sm[dev] = n;
+  return n;
 }
 
 }  // namespace pb200

@@ -67,12 +67,17 @@ decode_tma_kernel(HmViews hv, int N, int J, int H, int W, const double* __restri
       [&](int, int) {});
 }
 
-__global__ void crop_affine_kernel(const void* center, int c_f64, const void* scale, int s_f64, int n,
-                                   int out_w, int out_h, int inv, double* __restrict__ out) {
+__global__ void crop_affine_kernel(const void* center, int c_f64, const void* scale, int s_f64,
+                                   const double* __restrict__ rot_sincos, double shift_x, double shift_y,
+                                   int shift_f64, int n, int out_w, int out_h, int inv,
+                                   double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  CropSpec q = crop_spec_plain();
+  if (rot_sincos != nullptr) { q.sn = rot_sincos[2 * i]; q.cs = rot_sincos[2 * i + 1]; }
+  q.shift[0] = shift_x; q.shift[1] = shift_y; q.shift_f64 = shift_f64 != 0;
   double m[6];
-  crop_affine_row(center, c_f64, scale, s_f64, i, out_w, out_h, inv, m);
+  crop_affine_row(center, c_f64, scale, s_f64, i, q, out_w, out_h, inv, m);
 #pragma unroll
   for (int k = 0; k < 6; ++k) out[6 * (size_t)i + k] = m[k];
 }
@@ -99,14 +104,17 @@ bool views_vec_ok(const HmViews& hv, int HW) {
 using namespace pb200;
 
 extern "C" int pb200_crop_affine(const void* center, int center_dtype, const void* scale,
-                                 int scale_dtype, int n, int out_w, int out_h, int inv, double* out,
-                                 void* stream) {
+                                 int scale_dtype, const double* rot_sincos, double shift_x,
+                                 double shift_y, int shift_dtype, int n, int out_w, int out_h, int inv,
+                                 double* out, void* stream) {
   PB_REQUIRE(center && scale && out, "null pointer");
   PB_REQUIRE(n >= 0 && out_w > 0 && out_h > 0, "bad sizes n=%d out=(%d,%d)", n, out_w, out_h);
-  PB_REQUIRE((center_dtype | 1) == 1 && (scale_dtype | 1) == 1, "dtype tags must be PB200_F32/PB200_F64");
+  PB_REQUIRE((center_dtype | 1) == 1 && (scale_dtype | 1) == 1 && (shift_dtype | 1) == 1,
+             "dtype tags must be PB200_F32/PB200_F64");
   if (n == 0) return PB200_OK;
   crop_affine_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      center, center_dtype, scale, scale_dtype, n, out_w, out_h, inv, out);
+      center, center_dtype, scale, scale_dtype, rot_sincos, shift_x, shift_y, shift_dtype, n, out_w, out_h,
+      inv, out);
   PB_LAUNCH_CHECK("crop_affine_kernel");
   return PB200_OK;
 }
@@ -138,29 +146,33 @@ int pb200::launch_decode(const HmViews& hv, int N, int J, int H, int W, const do
   PB_REQUIRE(maps < (1LL << 31) - (1 << 20), "N*J too large for one launch; split the batch");
   if (views_vec_ok(hv, H * W)) {  // TMA ring front end
     const size_t smem = tma_ring_smem_bytes(kDecodeWarps);
-    static int blocks_per_sm_tma = 0;
-    if (blocks_per_sm_tma == 0) {
+    static PerDevice<int> tma_blocks_per_sm;
+    int* per_sm = tma_blocks_per_sm.slot();
+    if (per_sm == nullptr) return PB200_ERR_CUDA;
+    if (*per_sm == 0) {
       PB_CUDA(cudaFuncSetAttribute(decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int n = 0;
       PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, decode_tma_kernel, kDecodeWarps * 32, smem));
-      blocks_per_sm_tma = n > 0 ? n : 1;
+      *per_sm = n > 0 ? n : 1;
     }
     long long blocks = (maps + kDecodeWarps - 1) / kDecodeWarps;
-    const long long cap = (long long)sm * blocks_per_sm_tma;
+    const long long cap = (long long)sm * *per_sm;
     if (blocks > cap) blocks = cap;
     decode_tma_kernel<<<(unsigned)blocks, kDecodeWarps * 32, smem, (cudaStream_t)stream>>>(
         hv, N, J, H, W, affine, post_process, out_xy, out_maxval, out_idx);
     PB_LAUNCH_CHECK("decode_tma_kernel");
     return PB200_OK;
   }
-  static int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
+  static PerDevice<int> ldg_blocks_per_sm;
+  int* per_sm = ldg_blocks_per_sm.slot();
+  if (per_sm == nullptr) return PB200_ERR_CUDA;
+  if (*per_sm == 0) {
     int n = 0;
     PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, decode_kernel, kDecodeWarps * 32, 0));
-    blocks_per_sm = n > 0 ? n : 1;
+    *per_sm = n > 0 ? n : 1;
   }
   long long blocks = (maps + kDecodeWarps - 1) / kDecodeWarps;
-  const long long cap = (long long)sm * blocks_per_sm;  // one resident wave
+  const long long cap = (long long)sm * *per_sm;  // one resident wave
   if (blocks > cap) blocks = cap;
   decode_kernel<<<(unsigned)blocks, kDecodeWarps * 32, 0, (cudaStream_t)stream>>>(
       hv, N, J, H, W, views_vec_ok(hv, H * W) ? 1 : 0, affine, post_process, out_xy, out_maxval,

@@ -194,7 +194,7 @@ __global__ void project_kernel(const double* __restrict__ campack, int cam_id,
   load_cam(campack + (size_t)cam_id * PB200_CAM_STRIDE, c);
   const double X[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
   double u, v;
-  if (model == 0) project_h36m(c, X, u, v);
+  if (model == 0 || model == 3) project_h36m(c, X, u, v, model == 3);
   else project_plumb_bob(c, X, model == 1, u, v);
   out[2 * i] = u;
   out[2 * i + 1] = v;
@@ -298,7 +298,7 @@ static int launch_geo(const GeoParams& p, int xy_dtype, void* stream) {
   return PB200_OK;
 }
 
-// The lifting half of the two-kernel lift path (lift_fused.cu, variant 2): triangulate and
+// The lifting half of pb200_lift_fused (lift_fused.cu): triangulate and
 // reproject the float32 coordinates the decode kernel just wrote.
 int launch_lift_after_decode(const double* campack, const int32_t* cam_index, const float* xy,
                              const float* maxval, int use_conf, float conf_thre, int B, int V, int J,
@@ -317,7 +317,7 @@ extern "C" int pb200_project(const double* campack, int cam_id, const double* pt
                              double* out, void* stream) {
   PB_REQUIRE(campack && pts && out, "null pointer");
   PB_REQUIRE(n >= 0 && cam_id >= 0, "bad n=%d cam_id=%d", n, cam_id);
-  PB_REQUIRE(model >= 0 && model <= 2, "model must be 0 (h36m), 1 (plumb-bob) or 2 (pin-hole)");
+  PB_REQUIRE(model >= 0 && model <= 3, "model must be 0 (h36m), 1 (plumb-bob), 2 (pin-hole) or 3 (h36m, fx/fy)");
   if (n == 0) return PB200_OK;
   project_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(campack, cam_id, pts, n, model, out);
   PB_LAUNCH_CHECK("project_kernel");
@@ -397,8 +397,10 @@ extern "C" int pb200_mpjpe_stats(const double* pred, const double* gt, int B, in
   PB_REQUIRE(B >= 0 && J >= 1, "bad shape");
   const long long n = (long long)B * J;
   if (n == 0) return PB200_OK;
+  const int sm = cached_sm_count();
+  if (sm <= 0) return PB200_ERR_CUDA;
   long long blocks = (n + 255) / 256;
-  const long long cap = (long long)cached_sm_count() * 8;
+  const long long cap = (long long)sm * 8;
   if (blocks > cap) blocks = cap;
   mpjpe_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, n, out4);
   PB_LAUNCH_CHECK("mpjpe_kernel");

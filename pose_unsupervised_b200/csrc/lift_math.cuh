@@ -54,7 +54,10 @@ PB_HD void world_to_cam(const Cam& c, const double X[3], double xc[3]) {
 // H36M projection with averaged focal length (lib/multiviews/cameras.py:25-54).
 // Operation order follows the numpy expression so results track the reference
 // to the last bits (the 3x3 product is the one place numpy goes through BLAS).
-PB_HD void project_h36m(const Cam& c, const double X[3], double& u_px, double& v_px) {
+// separate_f: `f` = [fx, fy] (unfold_camera_param(camera, avg_f=False), cameras.py:17-18) instead
+// of the averaged focal length project_pose uses.
+PB_HD void project_h36m(const Cam& c, const double X[3], double& u_px, double& v_px,
+                        bool separate_f = false) {
   double xc[3];
   world_to_cam(c, X, xc);
   const double u = xc[0] / xc[2], v = xc[1] / xc[2];
@@ -62,8 +65,8 @@ PB_HD void project_h36m(const Cam& c, const double X[3], double& u_px, double& v
   const double poly = (c.k[0] * r2 + c.k[1] * (r2 * r2)) + c.k[2] * (r2 * r2 * r2);
   const double gain = (1.0 + poly) + (c.p[0] * v + c.p[1] * u);
   const double f = 0.5 * (c.fx + c.fy);
-  u_px = f * (u * gain + c.p[1] * r2) + c.cx;
-  v_px = f * (v * gain + c.p[0] * r2) + c.cy;
+  u_px = (separate_f ? c.fx : f) * (u * gain + c.p[1] * r2) + c.cx;
+  v_px = (separate_f ? c.fy : f) * (v * gain + c.p[0] * r2) + c.cy;
 }
 
 // pymvg find2d: pin-hole, OpenCV plumb-bob distortion, separate fx / fy
@@ -235,17 +238,43 @@ PB_HD void dlt_solve(const Sym4& g, double X[3]) {
 }
 
 // ---------------------------------------------------------------------------
-// Crop affine (lib/utils/transforms.py:76-109, rot = 0): float32 point triples,
-// then cv2.getAffineTransform's 6x6 elimination with partial pivoting in float64.
+// Crop affine (lib/utils/transforms.py:76-109): float32 point triples, then
+// cv2.getAffineTransform's 6x6 elimination with partial pivoting in float64.
 // ---------------------------------------------------------------------------
-PB_HD void crop_affine_points(double cx, double cy, double src_w, float S[3][2], int out_w,
-                              int out_h, float D[3][2]) {
-  // src[0] = center ; src[1] = center + [0, -src_w/2]   (sums in float64, stored float32)
-  S[0][0] = (float)cx;
-  S[0][1] = (float)cy;
-  S[1][0] = (float)(cx + 0.0);
-  S[1][1] = (float)(cy + src_w * -0.5);
-  // get_3rd_point: float32 arithmetic
+// What get_affine_transform is given besides centre and scale.  numpy's promotion rules decide in
+// which precision each sum of :94-95 is rounded before it is stored into the float32 `src` array,
+// so the dtypes travel with the values.
+struct CropSpec {
+  double sn, cs;       // np.sin / np.cos of np.pi * rot / 180, evaluated on the host (float64)
+  double shift[2];     // `shift` (default float32 zeros)
+  bool shift_f64;
+};
+
+PB_HD CropSpec crop_spec_plain() {
+  CropSpec q;
+  q.sn = 0.0; q.cs = 1.0; q.shift[0] = q.shift[1] = 0.0; q.shift_f64 = false;
+  return q;
+}
+
+// scale_px = scale * 200.0 in the dtype of `scale` (:84), returned as doubles
+PB_HD void crop_points(double cx, double cy, bool c_f64, double sw, double sh, bool s_f64,
+                       const CropSpec& q, float S[3][2], int out_w, int out_h, float D[3][2]) {
+  // t = scale_px * shift: float32 product unless either operand is float64
+  double tx, ty;
+  const bool t_f64 = s_f64 || q.shift_f64;
+  if (t_f64) { tx = sw * q.shift[0]; ty = sh * q.shift[1]; }
+  else { tx = (double)((float)sw * (float)q.shift[0]); ty = (double)((float)sh * (float)q.shift[1]); }
+  // src[0] = center + t (:94): one float32 add when both are float32, else float64
+  if (c_f64 || t_f64) { S[0][0] = (float)(cx + tx); S[0][1] = (float)(cy + ty); }
+  else { S[0][0] = (float)cx + (float)tx; S[0][1] = (float)cy + (float)ty; }
+  // src_dir = get_dir([0, src_w * -0.5], rot_rad) (:88,128-135): products with the float64 sin/cos
+  const double half = sw * -0.5;
+  const double dir0 = 0.0 * q.cs - half * q.sn;
+  const double dir1 = 0.0 * q.sn + half * q.cs;
+  // src[1] = center + src_dir + t (:95): `center + list of float64` is float64 whatever center is
+  S[1][0] = (float)((cx + dir0) + tx);
+  S[1][1] = (float)((cy + dir1) + ty);
+  // get_3rd_point (:123-125): float32 arithmetic
   const float dsx = S[0][0] - S[1][0], dsy = S[0][1] - S[1][1];
   S[2][0] = S[1][0] + (-dsy);
   S[2][1] = S[1][1] + dsx;
@@ -295,19 +324,20 @@ PB_HD void affine_from_triples(const float frm[3][2], const float to[3][2], doub
   for (int i = 0; i < 6; ++i) m[i] = b[i];
 }
 
-// src_w = (scale * 200)[0] in the dtype of `scale` (lib/utils/transforms.py:84-85)
-PB_HD double crop_src_w(const void* scale, int is_f64, int row) {
-  if (is_f64) return ((const double*)scale)[2 * row] * 200.0;
-  return (double)(((const float*)scale)[2 * row] * 200.0f);
+// (scale * 200.0)[k] in the dtype of `scale` (lib/utils/transforms.py:84-85)
+PB_HD double crop_scale_px(const void* scale, int is_f64, int row, int k) {
+  if (is_f64) return ((const double*)scale)[2 * row + k] * 200.0;
+  return (double)(((const float*)scale)[2 * row + k] * 200.0f);
 }
 
 PB_HD void crop_affine_row(const void* center, int c_f64, const void* scale, int s_f64, int row,
-                           int out_w, int out_h, int inv, double m[6]) {
+                           const CropSpec& q, int out_w, int out_h, int inv, double m[6]) {
   double cx, cy;
   if (c_f64) { cx = ((const double*)center)[2 * row]; cy = ((const double*)center)[2 * row + 1]; }
   else { cx = (double)((const float*)center)[2 * row]; cy = (double)((const float*)center)[2 * row + 1]; }
   float S[3][2], D[3][2];
-  crop_affine_points(cx, cy, crop_src_w(scale, s_f64, row), S, out_w, out_h, D);
+  crop_points(cx, cy, c_f64 != 0, crop_scale_px(scale, s_f64, row, 0), crop_scale_px(scale, s_f64, row, 1),
+              s_f64 != 0, q, S, out_w, out_h, D);
   if (inv) affine_from_triples(D, S, m);
   else affine_from_triples(S, D, m);
 }

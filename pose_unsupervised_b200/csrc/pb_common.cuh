@@ -40,8 +40,21 @@ void set_error(const char* fmt, ...);
     }                                                                              \
   } while (0)
 
-// cached per process; the library is used with one device per process
-int cached_sm_count();
+// Per-device caches: attributes set with cudaFuncSetAttribute and occupancy answers belong to
+// the CURRENT device, and one process may drive several (tests, notebooks, torch.cuda.set_device).
+constexpr int kMaxDevices = 64;
+int current_device_ordinal();   // -1 (and the error text set) when there is none
+int cached_sm_count();          // SM count of the current device, -1 on failure
+
+// One value per device ordinal, zero-initialised; `slot()` is null when there is no device.
+template <typename T>
+struct PerDevice {
+  T v[kMaxDevices];
+  T* slot() {
+    const int d = current_device_ordinal();
+    return d < 0 ? nullptr : &v[d];
+  }
+};
 
 struct HmViews {
   const float* ptr[PB200_MAX_VIEWS];

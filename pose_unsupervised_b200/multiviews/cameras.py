@@ -82,6 +82,15 @@ def _project(x, camera, model):
     return out if rt.is_device_tensor(x) else rt.to_host(out)
 
 
+def project_point_radial(x, R, T, f, c, k, p):
+    """lib/multiviews/cameras.py:25-49 on unfolded parameters: ``f`` is the averaged focal length
+    (shape (1,), what ``project_pose`` passes) or ``[fx, fy]`` (``unfold_camera_param(avg_f=False)``)."""
+    f = np.asarray(f, dtype=np.float64).reshape(-1)
+    c = np.asarray(c, dtype=np.float64).reshape(-1)
+    camera = {'R': R, 'T': T, 'fx': f[:1], 'fy': f[-1:], 'cx': c[:1], 'cy': c[1:2], 'k': k, 'p': p}
+    return _project(x, camera, 0 if f.size == 1 else 3)
+
+
 def project_pose(x, camera):
     """lib/multiviews/cameras.py:25-54: world [n,3] -> pixels [n,2], averaged focal length."""
     return _project(x, camera, 0)

@@ -2,9 +2,8 @@
 lib/multiviews/triangulate.py:57-213, plus the fused heatmap -> 3D pass.
 
 The reference builds a pymvg camera rig per frame and loops frames x joints in
-Python; here one CUDA thread owns one (frame, joint) (csrc/geometry.cu), or, for
-``lift_heatmaps``, the decode warps lift each frame as soon as its last heatmap has
-been decoded (csrc/lift_fused.cu).  ``nviews`` is a keyword (the reference
+Python; here one CUDA thread owns one (frame, joint) (csrc/geometry.cu); ``lift_heatmaps``
+runs the decode and that per-joint lift back to back on the device (csrc/lift_fused.cu).  ``nviews`` is a keyword (the reference
 hard-codes 4 at triangulate.py:70,114,183).
 """
 import ctypes
@@ -93,6 +92,90 @@ class LiftResult(object):
                           f(self.reproj_err), f(self.proj2d), f(self.epipolar))
 
 
+def _lift_launch(views, B, nviews, J, H, W, affine, post_process, pack, index, no_distortion, conf_thre,
+                 xy, maxvals, idx, poses3d, err, proj, fmat, slots, resid):
+    """One pb200_lift_fused call on device tensors (outputs preallocated by the caller)."""
+    ptrs = (ctypes.c_void_p * len(views))(*[v.data_ptr() for v in views])
+    _lib.call('pb200_lift_fused', ptrs, len(views), B, nviews, J, H, W, rt.ptr(affine),
+              int(bool(post_process)), rt.ptr(pack), rt.ptr(index),
+              int(bool(no_distortion)), int(conf_thre is not None),
+              float(0.0 if conf_thre is None else conf_thre),
+              rt.ptr(xy), rt.ptr(maxvals), rt.ptr(idx), rt.ptr(poses3d), rt.ptr(err), rt.ptr(proj),
+              rt.ptr(fmat), rt.ptr(slots), rt.ptr(resid), rt.stream_ptr())
+
+
+# Host heatmaps in pageable memory are staged through two pinned buffers in chunks of this many
+# bytes: the host copy of chunk k+1 runs while chunk k crosses PCIe and chunk k-1 is decoded.
+STAGE_BYTES = 256 << 20
+PAGEABLE_MIN_BYTES = 64 << 20     # smaller arrays go over in one plain copy
+_stage = {}
+
+
+def _staging(nbytes):
+    key = torch.cuda.current_device()
+    st = _stage.get(key)
+    if st is None or st['pinned'][0].numel() < nbytes:
+        st = {'pinned': [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)],
+              'device': [torch.empty(nbytes, dtype=torch.uint8, device=rt.device()) for _ in range(2)],
+              'copy_stream': torch.cuda.Stream(),
+              'h2d_done': [torch.cuda.Event() for _ in range(2)],
+              'lift_done': [torch.cuda.Event() for _ in range(2)],
+              'pool': None}
+        _stage[key] = st
+    return st
+
+
+def _host_copy(dst, src, pool, nthreads):
+    """memcpy of a large numpy block with several threads (numpy releases the GIL while copying)."""
+    n = src.shape[0]
+    if pool is None or n < 2 * nthreads:
+        np.copyto(dst, src)
+        return
+    step = (n + nthreads - 1) // nthreads
+    futs = [pool.submit(np.copyto, dst[i:i + step], src[i:i + step]) for i in range(0, n, step)]
+    for f in futs:
+        f.result()
+
+
+def _lift_from_pageable(hm, B, nviews, J, H, W, affine, post_process, table, no_distortion, conf_thre,
+                        outs, fmat, slots):
+    """Chunked, double-buffered host -> device pipeline for pageable numpy heatmaps."""
+    import concurrent.futures
+    import os
+    xy, maxvals, idx, poses3d, err, proj, resid = outs
+    frame_bytes = nviews * J * H * W * 4
+    fpc = max(1, min(B, STAGE_BYTES // frame_bytes))             # frames per chunk
+    st = _staging(fpc * frame_bytes)
+    if st['pool'] is None:
+        st['pool'] = concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1))
+    nthreads = st['pool']._max_workers
+    main = torch.cuda.current_stream()
+    flat = hm.reshape(B, -1)
+    for c, lo in enumerate(range(0, B, fpc)):
+        hi = min(B, lo + fpc)
+        s = c & 1
+        n = hi - lo
+        pinned = st['pinned'][s][:n * frame_bytes].view(torch.float32).view(n, -1)
+        dev = st['device'][s][:n * frame_bytes].view(torch.float32)
+        st['h2d_done'][s].synchronize()                           # pinned buffer s is free again
+        _host_copy(pinned.numpy(), flat[lo:hi], st['pool'], nthreads)
+        with torch.cuda.stream(st['copy_stream']):
+            if c >= 2:
+                st['copy_stream'].wait_event(st['lift_done'][s])  # device buffer s has been decoded
+            else:
+                st['copy_stream'].wait_stream(main)
+            dev.copy_(pinned.view(-1), non_blocking=True)
+            st['h2d_done'][s].record(st['copy_stream'])
+        main.wait_event(st['h2d_done'][s])
+        r0, r1 = lo * nviews, hi * nviews
+        _lift_launch([dev.view(n * nviews, J, H, W)], n, nviews, J, H, W, affine[r0:r1], post_process,
+                     table.pack, table.index[r0:r1], no_distortion, conf_thre,
+                     xy[r0:r1], maxvals[r0:r1], None if idx is None else idx[r0:r1], poses3d[lo:hi],
+                     err[r0:r1], None if proj is None else proj[r0:r1], fmat,
+                     None if slots is None else slots[lo:hi], None if resid is None else resid[lo:hi])
+        st['lift_done'][s].record(main)
+
+
 def lift_heatmaps(heatmaps, center, scale, camera_params, nviews=4, post_process=True,
                   no_distortion=False, conf_thre=None, return_idx=False, return_proj=False,
                   affine=None, out_poses3d=None, fundamental=None, subjects=None):
@@ -108,9 +191,23 @@ def lift_heatmaps(heatmaps, center, scale, camera_params, nviews=4, post_process
     send buffer of ``parallel.PoseExchange``).  With ``fundamental`` (a ``core.loss.FundamentalTable``)
     and ``subjects`` [B], the algebraic epipolar residuals of the decoded coordinates
     (run/test/test_fund_mtx.py:56-69) are produced in the same pass as ``result.epipolar``.
+
+    A numpy array in pageable host memory (what ``validate()`` hands over after ``.cpu().numpy()``,
+    lib/core/function.py:633-640) is streamed to the device in chunks through two pinned staging
+    buffers, so the host copy, the PCIe transfer and the decode of consecutive chunks overlap;
+    pinned arrays and CPU tensors go over in one asynchronous copy.
     """
     rt.require_device()
-    views, N, J, H, W = _view_pointers(heatmaps)
+    pageable = None
+    if isinstance(heatmaps, np.ndarray) and heatmaps.ndim == 4 and heatmaps.dtype == np.float32 \
+            and heatmaps.flags['C_CONTIGUOUS'] and heatmaps.flags['WRITEABLE'] \
+            and heatmaps.nbytes >= PAGEABLE_MIN_BYTES and heatmaps.shape[0] % nviews == 0 \
+            and heatmaps.shape[0] > 0 and not torch.from_numpy(heatmaps).is_pinned():
+        pageable = heatmaps
+        N, J, H, W = [int(v) for v in heatmaps.shape]
+        views = [None]
+    else:
+        views, N, J, H, W = _view_pointers(heatmaps)
     if N % nviews != 0:
         raise ValueError('%d rows are not a multiple of nviews=%d' % (N, nviews))
     if len(views) not in (1, nviews):
@@ -143,14 +240,12 @@ def lift_heatmaps(heatmaps, center, scale, camera_params, nviews=4, post_process
         if int(slots.shape[0]) != B or fundamental.nviews != nviews:
             raise ValueError('fundamental table / subjects do not match the batch')
         resid = rt.empty((B, nviews * (nviews - 1), J), torch.float64)
-    ws = rt.workspace('lift', _lib.load().pb200_lift_workspace_bytes(B, nviews, J))
-    ptrs = (ctypes.c_void_p * len(views))(*[v.data_ptr() for v in views])
-    _lib.call('pb200_lift_fused', ptrs, len(views), B, nviews, J, H, W, rt.ptr(affine),
-              int(bool(post_process)), rt.ptr(table.pack), rt.ptr(table.index),
-              int(bool(no_distortion)), int(conf_thre is not None),
-              float(0.0 if conf_thre is None else conf_thre),
-              rt.ptr(xy), rt.ptr(maxvals), rt.ptr(idx), rt.ptr(poses3d), rt.ptr(err), rt.ptr(proj),
-              rt.ptr(fmat), rt.ptr(slots), rt.ptr(resid), rt.ptr(ws), rt.stream_ptr())
+    if pageable is not None:
+        _lift_from_pageable(pageable, B, nviews, J, H, W, affine.view(N, 6), post_process, table,
+                            no_distortion, conf_thre, (xy, maxvals, idx, poses3d, err, proj, resid), fmat, slots)
+    else:
+        _lift_launch(views, B, nviews, J, H, W, affine, post_process, table.pack, table.index, no_distortion,
+                     conf_thre, xy, maxvals, idx, poses3d, err, proj, fmat, slots, resid)
     return LiftResult(xy, maxvals, idx, poses3d, err, proj, resid)
 
 

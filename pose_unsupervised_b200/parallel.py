@@ -67,40 +67,93 @@ class PoseExchange(object):
     ``mpjpe_stats`` accumulates (``stats_view``), so nothing is copied before the all-gather;
     buffers are allocated once, which also makes the whole step capturable in a CUDA graph.
     Shards may be uneven (the last rank takes the remainder): every rank sends ``cap`` frames.
+
+    ``nslots`` > 1 gives independent send/receive buffers: with two slots the all-gather of step
+    k-1 runs on a side stream underneath the kernels of step k (``pipelined_step``), so the
+    collective's latency leaves the critical path.
     """
 
-    def __init__(self, nframes, njoints, device, group=None, dtype=torch.float64):
+    def __init__(self, nframes, njoints, device, group=None, dtype=torch.float64, nslots=1):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.nframes, self.njoints = nframes, njoints
+        self.nframes, self.njoints, self.nslots = nframes, njoints, nslots
         self.counts = [hi - lo for lo, hi in (frame_shard(nframes, r, self.world) for r in range(self.world))]
         self.cap = max(self.counts)
         self.width = self.cap * njoints * 3 + 4
-        self.send = torch.zeros(self.width, dtype=dtype, device=device)
-        self.recv = torch.zeros(self.world * self.width, dtype=dtype, device=device)
+        self.send = [torch.zeros(self.width, dtype=dtype, device=device) for _ in range(nslots)]
+        self.recv = [torch.zeros(self.world * self.width, dtype=dtype, device=device) for _ in range(nslots)]
+        self.side = torch.cuda.Stream(device=device) if (device.type == 'cuda' and nslots > 1) else None
 
-    def poses_view(self):
+    def poses_view(self, slot=0):
         b = self.counts[self.rank]
-        return self.send[:b * self.njoints * 3].view(b, self.njoints, 3)
+        return self.send[slot][:b * self.njoints * 3].view(b, self.njoints, 3)
 
-    def stats_view(self):
-        return self.send[self.width - 4:]
+    def stats_view(self, slot=0):
+        return self.send[slot][self.width - 4:]
 
-    def run(self):
+    def run(self, slot=0):
+        """All-gather of slot ``slot`` on the current stream."""
         if self.world > 1:
-            dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+            dist.all_gather_into_tensor(self.recv[slot], self.send[slot], group=self.group)
         else:
-            self.recv.copy_(self.send)
+            self.recv[slot].copy_(self.send[slot])
 
-    def gathered_poses(self):
-        rows = self.recv.view(self.world, self.width)
+    def pipelined_step(self, k, compute):
+        """Step ``k`` of a double-buffered loop: ``compute(slot)`` fills slot ``k % nslots`` on the
+        current stream while the all-gather of the previous step's slot runs on the side stream.
+        Fork and join are stream waits, so the step is capturable in a CUDA graph (one graph per
+        slot).  The last step's slot is still to be gathered afterwards: ``run((K-1) % nslots)``.
+        """
+        cur, prev = k % self.nslots, (k - 1) % self.nslots
+        if self.world == 1:
+            return compute(cur)
+        if self.side is None:                       # CPU tensors (gloo tests): same order, no overlap
+            self.run(prev)
+            return compute(cur)
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)                 # fork: step k-1 has finished on `main`
+        with torch.cuda.stream(self.side):
+            self.run(prev)
+        out = compute(cur)
+        main.wait_stream(self.side)                 # join
+        return out
+
+    def gathered_poses(self, slot=0):
+        rows = self.recv[slot].view(self.world, self.width)
         return torch.cat([rows[r, :self.counts[r] * self.njoints * 3].view(self.counts[r], self.njoints, 3)
                           for r in range(self.world)], dim=0)
 
-    def reduced_stats(self):
-        st = self.recv.view(self.world, self.width)[:, self.width - 4:]
+    def reduced_stats(self, slot=0):
+        st = self.recv[slot].view(self.world, self.width)[:, self.width - 4:]
         return torch.stack([st[:, 0].sum(), st[:, 1].sum(), st[:, 2].max(), st[:, 3].sum()])
+
+
+def shutdown(timeout_s=20.0):
+    """Leave the process group without hanging: callers drop every CUDA graph that captured a
+    collective first (NCCL's communicator teardown waits for them), then this barriers, syncs and
+    destroys the group under a watchdog that ends the process if teardown does not return."""
+    import gc
+    import os
+    import sys
+    import threading
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if not dist.is_initialized():
+        return
+    dog = threading.Timer(timeout_s, lambda: os._exit(0))
+    dog.daemon = True
+    dog.start()
+    try:
+        dist.barrier()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        dist.destroy_process_group()
+    finally:
+        dog.cancel()
 
 
 def max_over_ranks(value, device, group=None):

@@ -1,11 +1,10 @@
 """Crop affine <-> heatmap pixels, behind the names of lib/utils/transforms.py:67-135.
 
 ``get_affine_transform`` / ``transform_preds`` run the crop-affine kernel
-(csrc/lift_math.cuh::crop_affine_row, bit-identical to cv2.getAffineTransform on
-the reference's float32 point triples).  Only the configuration the lifting path
-uses is implemented: ``rot == 0`` and ``shift == 0`` (lib/core/inference.py:70-73,
-lib/multiviews/pictorial.py:169-170); data-augmentation rotations stay with the
-reference's own module.
+(csrc/lift_math.cuh::crop_affine_row, bit-identical to the reference's float32 point
+triples + cv2.getAffineTransform, rotations and shifts included -- pinned by
+tests/golden/affine.npz).  ``crop_affine`` is the batched device form the lifting path
+uses (one launch for all rows of a batch).
 """
 import numpy as np
 import torch
@@ -13,11 +12,13 @@ import torch
 from .. import _lib, runtime as rt
 
 
-def crop_affine(center, scale, output_size, inv=0):
+def crop_affine(center, scale, output_size, inv=0, rot=None, shift=None):
     """Batched crop affine on the device: center [n,2], scale [n,2] -> CUDA tensor [n,2,3] float64.
 
     center / scale keep their float32 or float64 dtype: the reference's arithmetic
     depends on it (``scale * 200.0`` is rounded in the dtype of ``scale``).
+    rot: degrees, a scalar or [n] (``None`` / 0 = the lifting path's unrotated crop);
+    shift: the reference's ``shift`` [2] (default float32 zeros).
     """
     rt.require_device()
     c = rt.to_device_float(center).reshape(-1, 2)
@@ -25,22 +26,31 @@ def crop_affine(center, scale, output_size, inv=0):
     if c.shape != s.shape:
         raise ValueError('center %s and scale %s must both be [n, 2]' % (tuple(c.shape), tuple(s.shape)))
     n = c.shape[0]
+    sincos = None
+    if rot is not None and np.any(np.asarray(rot) != 0):
+        # np.sin / np.cos of the float64 angle on the host, like lib/utils/transforms.py:87,129
+        rad = np.pi * np.broadcast_to(np.asarray(rot, dtype=np.float64).reshape(-1), (n,)) / 180
+        sincos = rt.to_device(np.stack([np.sin(rad), np.cos(rad)], axis=1))
+    sh = np.zeros(2, dtype=np.float32) if shift is None else np.asarray(shift).reshape(2)
+    sh_tag = _lib.F64 if sh.dtype == np.float64 or sh.dtype.kind in 'iu' else _lib.F32
+    if sh.dtype not in (np.float32, np.float64):
+        sh = sh.astype(np.float64)
     out = rt.empty((n, 2, 3), torch.float64)
     _lib.call('pb200_crop_affine', rt.ptr(c), rt.float_dtype_tag(c), rt.ptr(s), rt.float_dtype_tag(s),
+              rt.ptr(sincos), float(sh[0]), float(sh[1]), sh_tag,
               n, int(output_size[0]), int(output_size[1]), int(bool(inv)), rt.ptr(out), rt.stream_ptr())
     return out
 
 
 def get_affine_transform(center, scale, rot, output_size,
                          shift=np.array([0, 0], dtype=np.float32), inv=0):
-    """lib/utils/transforms.py:76-109 -> numpy [2,3] float64 (rot = 0, shift = 0 only)."""
-    if rot != 0 or np.any(np.asarray(shift) != 0):
-        raise NotImplementedError('only rot=0, shift=0 is on the lifting path (see module docstring)')
+    """lib/utils/transforms.py:76-109 -> numpy [2,3] float64."""
     if not isinstance(scale, np.ndarray) and not isinstance(scale, list):
         scale = np.array([scale, scale])                      # transforms.py:82-83
     center = np.asarray(center)
     scale = np.asarray(scale)
-    return rt.to_host(crop_affine(center.reshape(1, 2), scale.reshape(1, 2), output_size, inv))[0]
+    return rt.to_host(crop_affine(center.reshape(1, 2), scale.reshape(1, 2), output_size, inv,
+                                  rot=rot, shift=shift))[0]
 
 
 def affine_transform(pt, t):

@@ -12,9 +12,15 @@ using namespace pb200;
 
 extern "C" {
 
-void hc_crop_affine(const void* center, int c_f64, const void* scale, int s_f64, int n, int out_w,
-                    int out_h, int inv, double* out) {
-  for (int i = 0; i < n; ++i) crop_affine_row(center, c_f64, scale, s_f64, i, out_w, out_h, inv, out + 6 * i);
+void hc_crop_affine(const void* center, int c_f64, const void* scale, int s_f64, const double* rot_sincos,
+                    double shift_x, double shift_y, int shift_f64, int n, int out_w, int out_h, int inv,
+                    double* out) {
+  for (int i = 0; i < n; ++i) {
+    CropSpec q = crop_spec_plain();
+    if (rot_sincos) { q.sn = rot_sincos[2 * i]; q.cs = rot_sincos[2 * i + 1]; }
+    q.shift[0] = shift_x; q.shift[1] = shift_y; q.shift_f64 = shift_f64 != 0;
+    crop_affine_row(center, c_f64, scale, s_f64, i, q, out_w, out_h, inv, out + 6 * i);
+  }
 }
 
 void hc_project(const double* campack, const double* pts, int n, int model, double* out) {

@@ -37,18 +37,53 @@ def P(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def _hc_affine(hc, c, s, rot, size, inv, shift=None):
+    out = np.zeros(6)
+    sincos = None
+    if rot != 0:
+        r = np.pi * rot / 180
+        sincos = np.array([np.sin(r), np.cos(r)])
+    sh = np.zeros(2, np.float32) if shift is None else shift
+    hc.hc_crop_affine.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                  ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    hc.hc_crop_affine(P(c), int(c.dtype == np.float64), P(s), int(s.dtype == np.float64),
+                      P(sincos) if sincos is not None else None, float(sh[0]), float(sh[1]),
+                      int(sh.dtype == np.float64), 1, int(size[0]), int(size[1]), inv, P(out))
+    return out
+
+
 def test_crop_affine_bit_exact(hc):
+    """Every golden matrix of the real get_affine_transform (cv2), rotated boxes included."""
     a = golden('affine.npz')
-    for i in np.where(a['rot'] == 0)[0]:
+    assert (a['rot'] != 0).sum() >= 32
+    for i in range(len(a['rot'])):
         c = np.ascontiguousarray(a['center'][i:i + 1])
         s = np.ascontiguousarray(a['scale'][i:i + 1])
         if a['f32'][i]:
             c, s = c.astype(np.float32), s.astype(np.float32)
         for inv in (0, 1):
-            out = np.zeros(6)
-            hc.hc_crop_affine(P(c), int(c.dtype == np.float64), P(s), int(s.dtype == np.float64), 1,
-                              int(a['size'][i][0]), int(a['size'][i][1]), inv, P(out))
+            out = _hc_affine(hc, c, s, float(a['rot'][i]), a['size'][i], inv)
             assert np.array_equal(out, a['inv' if inv else 'fwd'][i].ravel()), (i, inv)
+
+
+def test_crop_affine_shift_matches_oracle(hc):
+    """`shift` != 0 (never used by the reference's callers, but part of the signature): every
+    dtype combination against the oracle restatement, which is itself pinned by affine.npz."""
+    from oracle import transforms as otr
+    rng = np.random.default_rng(5)
+    for trial in range(64):
+        cd = np.float32 if trial & 1 else np.float64
+        sd = np.float32 if trial & 2 else np.float64
+        hd = np.float32 if trial & 4 else np.float64
+        c = rng.uniform(100, 900, (1, 2)).astype(cd)
+        s = np.repeat(rng.uniform(0.5, 4.0, (1, 1)), 2, 1).astype(sd)
+        sh = rng.uniform(-0.3, 0.3, 2).astype(hd)
+        rot = float(rng.uniform(-45, 45)) if trial & 8 else 0.0
+        for inv in (0, 1):
+            ref = otr.get_affine_transform(c[0], s[0], rot, [64, 48], shift=sh, inv=inv)
+            out = _hc_affine(hc, c, s, rot, (64, 48), inv, shift=sh)
+            assert np.array_equal(out, ref.ravel()), (trial, inv)
 
 
 def test_project_h36m_vs_reference(hc):
@@ -78,7 +113,7 @@ def test_unary_and_grid_vs_reference(hc):
             aff = np.zeros(6)
             cc = np.ascontiguousarray(r['f%d_box_center' % f][v:v + 1])
             ss = np.ascontiguousarray(r['f%d_box_scale' % f][v:v + 1])
-            hc.hc_crop_affine(P(cc), 1, P(ss), 1, 1, 256, 256, 0, P(aff))
+            aff[:] = _hc_affine(hc, cc, ss, 0.0, (256, 256), 0)
             for j in range(16):
                 o = np.zeros(4096)
                 h = np.ascontiguousarray(hm[v, j])

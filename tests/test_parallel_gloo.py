@@ -41,6 +41,17 @@ def _worker(rank, world, port, nframes, q):
         ex.run()
         red2 = ex.reduced_stats()
         assert torch.equal(ex.gathered_poses(), pred) and torch.allclose(red2, red)
+        # double-buffered form: the gather of step k-1 is issued in step k, the last one drained
+        ex2 = parallel.PoseExchange(nframes, 17, torch.device('cpu'), nslots=2)
+        for k in range(3):
+            def compute(slot, k=k):
+                ex2.poses_view(slot).copy_(pred[lo:hi] + k)
+                ex2.stats_view(slot).copy_(stats)
+            ex2.pipelined_step(k, compute)
+            if k >= 1:
+                assert torch.equal(ex2.gathered_poses((k - 1) % 2), pred + (k - 1))
+        ex2.run(2 % 2)
+        assert torch.equal(ex2.gathered_poses(0), pred + 2) and torch.allclose(ex2.reduced_stats(0), red)
         all_err = (pred - gt).norm(dim=2)
         ok = torch.equal(full, pred) and abs(float(red[0]) - float(all_err.sum())) < 1e-6 \
             and float(red[2]) == float(all_err.max()) and float(red[3]) == all_err.numel() \
