@@ -229,6 +229,13 @@ int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, int B, int V,
                      const double* fmat, const int32_t* subj_index, double* out_resid,
                      void* stream);
 
+/* The lifting half of pb200_lift_fused on its own, for callers that put work between the two
+ * launches: xy [B*V,J,2] / maxval [B*V,J] float32 as written by pb200_decode; outputs as above. */
+int pb200_lift_decoded(const double* campack, const int32_t* cam_index, const float* xy,
+                       const float* maxval, int use_conf, float conf_thre, int B, int V, int J,
+                       int no_distortion, double* out_X, float* out_err, double* out_proj,
+                       const double* fmat, const int32_t* subj_index, double* out_resid, void* stream);
+
 /* ---- RPSM: recursive pictorial structure grid search -------------------------------
  * Replaces multiviews.pictorial.rpsm (lib/multiviews/pictorial.py:214-250) for a
  * batch of frames, one thread block per frame.
@@ -248,7 +255,12 @@ int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, int B, int V,
  *   use_lut   : 1 if pb200_pairwise_lut_check found the matrix to depend on the index offset
  *             (|dy|,|dx|,|dz|) only -- true for matrices generated on the regular grid; the
  *             kernel then keeps row 0 of each edge in shared memory instead of reading rows
- *   workspace : bytes from pb200_rpsm_workspace_bytes
+ *   max_reach : out_flag[1] of pb200_pairwise_lut_check (largest |bin offset| of an allowed pair),
+ *             or -1 if unknown.  With use_lut = 1, max_reach in [0, 5] and first_nbins <= 16 level 0
+ *             runs entirely on chip (heatmaps staged in shared memory by cp.async.bulk, energies in
+ *             shared memory, only uint16 back pointers written out); any other combination takes
+ *             the generic kernel.  Both give identical results.
+ *   workspace : bytes from pb200_rpsm_workspace_bytes, 256-byte aligned
  *   out_pose  [B,J,3] float64 ; out_trace [B, depth+1, J] int32 chosen bin per level (or NULL)
  */
 size_t pb200_rpsm_workspace_bytes(int B, int J, int first_nbins, int n_sm);
@@ -256,7 +268,7 @@ int pb200_rpsm(const float* hm, int B, int V, int J, int H, int W,
                const double* campack, const int32_t* cam_index, const double* box_affine,
                int img_w, int img_h, const double* root, const double* limb,
                const int32_t* edges, const int32_t* order, int root_idx,
-               const uint32_t* pair_bits, int use_lut,
+               const uint32_t* pair_bits, int use_lut, int max_reach,
                int first_nbins, int recur_nbins, int recur_depth, double grid_size, double tolerance,
                void* workspace, size_t workspace_bytes,
                double* out_pose, int32_t* out_trace, void* stream);
@@ -268,8 +280,9 @@ int pb200_rpsm(const float* hm, int B, int V, int J, int H, int W,
  */
 int pb200_pairwise_level0(const double* avg_limb, int E, int nbins, double box_size,
                           uint32_t* pair_bits, void* stream);
-/* *out_flag |= 1 (device int32, zeroed by the caller) unless every P_e[i,j] equals
- * P_e[0, (|dy|*n+|dx|)*n+|dz|], i.e. unless the bit matrix is a function of the offset only. */
+/* out_flag: device int32[2], zeroed by the caller.  out_flag[0] |= 1 unless every P_e[i,j] equals
+ * P_e[0, (|dy|*n+|dx|)*n+|dz|], i.e. unless the bit matrix is a function of the offset only;
+ * out_flag[1] = largest max(|dy|,|dx|,|dz|) over the allowed pairs of row 0 of any edge. */
 int pb200_pairwise_lut_check(const uint32_t* pair_bits, int E, int nbins, int32_t* out_flag,
                              void* stream);
 

@@ -55,9 +55,11 @@ _PROTOS = {
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p,
                                  c_void_p]),
+    'pb200_lift_decoded': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_int,
+                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'pb200_rpsm_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'pb200_rpsm': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                           c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                           c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                            c_int, c_int, c_int, c_double, c_double, c_void_p, c_size_t,
                            c_void_p, c_void_p, c_void_p]),
     'pb200_pairwise_level0': (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),

@@ -52,3 +52,23 @@ extern "C" int pb200_lift_fused(const float* const* hm_views_host, int n_ptr, in
                                   no_distortion, out_X, out_err, out_proj, fmat, subj_index, out_resid,
                                   stream);
 }
+
+// The second half on its own: triangulate + reproject (+ epipolar residuals) the float32 coordinates a
+// previous pb200_decode wrote, with joints_vis = maxval > conf_thre.  Callers that need to put work
+// between the two launches (parallel.PoseExchange forks the previous step's all-gather there, so that
+// it runs under this latency-bound kernel instead of competing with the HBM-bound decode) use
+// pb200_decode + pb200_lift_decoded; the results are those of pb200_lift_fused.
+extern "C" int pb200_lift_decoded(const double* campack, const int32_t* cam_index, const float* xy,
+                                  const float* maxval, int use_conf, float conf_thre, int B, int V, int J,
+                                  int no_distortion, double* out_X, float* out_err, double* out_proj,
+                                  const double* fmat, const int32_t* subj_index, double* out_resid,
+                                  void* stream) {
+  PB_REQUIRE(B >= 0 && J >= 1, "bad shape B=%d J=%d", B, J);
+  if (B == 0) return PB200_OK;
+  PB_REQUIRE(V >= 2 && V <= PB200_MAX_VIEWS, "V=%d outside [2,%d]", V, PB200_MAX_VIEWS);
+  PB_REQUIRE(campack && cam_index && xy && maxval, "null input pointer");
+  PB_REQUIRE(out_X && out_err, "null output pointer");
+  PB_REQUIRE(out_resid == nullptr || (fmat && subj_index), "out_resid needs fmat and subj_index");
+  return launch_lift_after_decode(campack, cam_index, xy, maxval, use_conf, conf_thre, B, V, J, no_distortion,
+                                  out_X, out_err, out_proj, fmat, subj_index, out_resid, stream);
+}

@@ -71,8 +71,8 @@ struct RpsmShared {
   double pose[kRpsmMaxJ][3];
   double limb[kRpsmMaxJ];
   int edge_p[kRpsmMaxJ], edge_c[kRpsmMaxJ], order[kRpsmMaxJ], bin[kRpsmMaxJ];
-  double red_val[kRpsmThreads / 32];
-  int red_idx[kRpsmThreads / 32];
+  double red_val[32];
+  int red_idx[32];
   int reach;
 };
 
@@ -140,6 +140,122 @@ __device__ __forceinline__ void sort_children(const double* __restrict__ Ec, uin
       }
       __syncthreads();
     }
+  }
+}
+
+// ---- refinement levels (pictorial.py:193-211, 243-248) -----------------------------------------
+// per-joint nR^3 grids centred on the current estimate; one thread per (view, joint, bin) sample,
+// ordered sum over views, limb predicate on the fly, tree max-product by warp 0.  s.pose holds
+// the level-0 estimate on entry and the final pose on exit.  Block-wide (T threads).
+template <int T>
+__device__ __forceinline__ void refine_levels(const RpsmParams& p, RpsmShared& s, int f, double* gp,
+                                              double* eR, double* sv, uint8_t* bpR) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int J = p.J, E = J - 1, V = p.V;
+  const int n0 = p.n0;
+  const int nR = p.nR, nbR = nR * nR * nR;
+  double cur = p.grid_size / (double)n0;
+  for (int lvl = 1; lvl <= p.depth; ++lvl) {
+    for (int t = tid; t < J * nbR; t += T) {
+      const int j = t / nbR, b = t - j * nbR;
+      double X[3];
+      bin_to_point(cur, nR, b, s.pose[j], X);
+      gp[3 * t] = X[0]; gp[3 * t + 1] = X[1]; gp[3 * t + 2] = X[2];
+    }
+    __syncthreads();
+    // one thread per (view, joint, bin) sample, then the ordered sum over views
+    for (int t = tid; t < V * J * nbR; t += T) {
+      const int v = t / (J * nbR), r = t - v * (J * nbR);
+      sv[t] = sample_view(p, s, f, v, r / nbR, gp + 3 * r);
+    }
+    __syncthreads();
+    for (int t = tid; t < J * nbR; t += T) {
+      double u = 0.0;
+      for (int v = 0; v < V; ++v) u = u + sv[v * (J * nbR) + t];
+      eR[t] = u;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int oi = 0; oi < J; ++oi) {
+        const int par = s.order[oi];
+        if (nbR == 8) {
+          // lanes = (parent bin i = lane/4) x (child bins 2q, 2q+1 with q = lane%4)
+          const int i = lane >> 2, q = lane & 3;
+          const double* gi = gp + 3 * (par * 8 + i);
+          double acc = eR[par * 8 + i];
+          for (int e = 0; e < E; ++e) {
+            if (s.edge_p[e] != par) continue;
+            const int c = s.edge_c[e];
+            double best = 0.0;
+            int bidx = -1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int jj = 2 * q + h;
+              const double* gj = gp + 3 * (c * 8 + jj);
+              const double dx = gi[0] - gj[0], dy = gi[1] - gj[1], dz = gi[2] - gj[2];
+              const double d = sqrt((dx * dx + dy * dy) + dz * dz);
+              const double val = (fabs(d - s.limb[e]) <= p.tol) ? eR[c * 8 + jj] : 0.0;
+              if (bidx < 0 || val > best) { best = val; bidx = jj; }
+            }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {  // merge the 4 lanes of this parent bin
+              const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+              const int ob = __shfl_xor_sync(0xffffffffu, bidx, o);
+              if (ov > best || (ov == best && ob < bidx)) { best = ov; bidx = ob; }
+            }
+            acc = acc * best;
+            if (q == 0) bpR[e * 8 + i] = (uint8_t)bidx;
+          }
+          __syncwarp();
+          if (q == 0) eR[par * 8 + i] = acc;
+        } else {
+          for (int i = lane; i < nbR; i += 32) {
+            const double* gi = gp + 3 * (par * nbR + i);
+            double acc = eR[par * nbR + i];
+            for (int e = 0; e < E; ++e) {
+              if (s.edge_p[e] != par) continue;
+              const int c = s.edge_c[e];
+              double best = 0.0;
+              int bidx = -1;
+              for (int jj = 0; jj < nbR; ++jj) {
+                const double* gj = gp + 3 * (c * nbR + jj);
+                const double dx = gi[0] - gj[0], dy = gi[1] - gj[1], dz = gi[2] - gj[2];
+                const double d = sqrt((dx * dx + dy * dy) + dz * dz);
+                const double val = (fabs(d - s.limb[e]) <= p.tol) ? eR[c * nbR + jj] : 0.0;
+                if (bidx < 0 || val > best) { best = val; bidx = jj; }
+              }
+              acc = acc * best;
+              bpR[e * nbR + i] = (uint8_t)bidx;
+            }
+            eR[par * nbR + i] = acc;
+          }
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        const double* er = eR + p.root_idx * nbR;
+        double best = er[0];
+        int bidx = 0;
+        for (int b = 1; b < nbR; ++b)
+          if (er[b] > best) { best = er[b]; bidx = b; }
+        s.bin[p.root_idx] = bidx;
+        for (int oi = J - 1; oi >= 0; --oi) {
+          const int par = s.order[oi];
+          for (int e = 0; e < E; ++e)
+            if (s.edge_p[e] == par) s.bin[s.edge_c[e]] = bpR[e * nbR + s.bin[par]];
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < J) {
+      const int b = s.bin[tid];
+      if (p.out_trace) p.out_trace[((size_t)f * (p.depth + 1) + lvl) * J + tid] = b;
+      const double* g = gp + 3 * (tid * nbR + b);
+      const double X0 = g[0], X1 = g[1], X2 = g[2];
+      s.pose[tid][0] = X0; s.pose[tid][1] = X1; s.pose[tid][2] = X2;
+    }
+    __syncthreads();
+    cur = cur / (double)nR;
   }
 }
 
@@ -389,115 +505,762 @@ __global__ void __launch_bounds__(kRpsmThreads, 2) rpsm_kernel(const RpsmParams 
       __syncthreads();
     }
 
-    // ---- refinement levels ----------------------------------------------------------
-    double cur = p.grid_size / (double)n0;
-    for (int lvl = 1; lvl <= p.depth; ++lvl) {
-      for (int t = tid; t < J * nbR; t += kRpsmThreads) {
-        const int j = t / nbR, b = t - j * nbR;
-        double X[3];
-        bin_to_point(cur, nR, b, s.pose[j], X);
-        gp[3 * t] = X[0]; gp[3 * t + 1] = X[1]; gp[3 * t + 2] = X[2];
-      }
-      __syncthreads();
-      // one thread per (view, joint, bin) sample, then the ordered sum over views
-      for (int t = tid; t < V * J * nbR; t += kRpsmThreads) {
-        const int v = t / (J * nbR), r = t - v * (J * nbR);
-        sv[t] = sample_view(p, s, f, v, r / nbR, gp + 3 * r);
-      }
-      __syncthreads();
-      for (int t = tid; t < J * nbR; t += kRpsmThreads) {
-        double u = 0.0;
-        for (int v = 0; v < V; ++v) u = u + sv[v * (J * nbR) + t];
-        eR[t] = u;
-      }
-      __syncthreads();
-      if (warp == 0) {
-        for (int oi = 0; oi < J; ++oi) {
-          const int par = s.order[oi];
-          if (nbR == 8) {
-            // lanes = (parent bin i = lane/4) x (child bins 2q, 2q+1 with q = lane%4)
-            const int i = lane >> 2, q = lane & 3;
-            const double* gi = gp + 3 * (par * 8 + i);
-            double acc = eR[par * 8 + i];
-            for (int e = 0; e < E; ++e) {
-              if (s.edge_p[e] != par) continue;
-              const int c = s.edge_c[e];
-              double best = 0.0;
-              int bidx = -1;
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int jj = 2 * q + h;
-                const double* gj = gp + 3 * (c * 8 + jj);
-                const double dx = gi[0] - gj[0], dy = gi[1] - gj[1], dz = gi[2] - gj[2];
-                const double d = sqrt((dx * dx + dy * dy) + dz * dz);
-                const double val = (fabs(d - s.limb[e]) <= p.tol) ? eR[c * 8 + jj] : 0.0;
-                if (bidx < 0 || val > best) { best = val; bidx = jj; }
-              }
-#pragma unroll
-              for (int o = 1; o <= 2; o <<= 1) {  // merge the 4 lanes of this parent bin
-                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int ob = __shfl_xor_sync(0xffffffffu, bidx, o);
-                if (ov > best || (ov == best && ob < bidx)) { best = ov; bidx = ob; }
-              }
-              acc = acc * best;
-              if (q == 0) bpR[e * 8 + i] = (uint8_t)bidx;
-            }
-            __syncwarp();
-            if (q == 0) eR[par * 8 + i] = acc;
-          } else {
-            for (int i = lane; i < nbR; i += 32) {
-              const double* gi = gp + 3 * (par * nbR + i);
-              double acc = eR[par * nbR + i];
-              for (int e = 0; e < E; ++e) {
-                if (s.edge_p[e] != par) continue;
-                const int c = s.edge_c[e];
-                double best = 0.0;
-                int bidx = -1;
-                for (int jj = 0; jj < nbR; ++jj) {
-                  const double* gj = gp + 3 * (c * nbR + jj);
-                  const double dx = gi[0] - gj[0], dy = gi[1] - gj[1], dz = gi[2] - gj[2];
-                  const double d = sqrt((dx * dx + dy * dy) + dz * dz);
-                  const double val = (fabs(d - s.limb[e]) <= p.tol) ? eR[c * nbR + jj] : 0.0;
-                  if (bidx < 0 || val > best) { best = val; bidx = jj; }
-                }
-                acc = acc * best;
-                bpR[e * nbR + i] = (uint8_t)bidx;
-              }
-              eR[par * nbR + i] = acc;
-            }
-          }
-          __syncwarp();
-        }
-        if (lane == 0) {
-          const double* er = eR + p.root_idx * nbR;
-          double best = er[0];
-          int bidx = 0;
-          for (int b = 1; b < nbR; ++b)
-            if (er[b] > best) { best = er[b]; bidx = b; }
-          s.bin[p.root_idx] = bidx;
-          for (int oi = J - 1; oi >= 0; --oi) {
-            const int par = s.order[oi];
-            for (int e = 0; e < E; ++e)
-              if (s.edge_p[e] == par) s.bin[s.edge_c[e]] = bpR[e * nbR + s.bin[par]];
-          }
-        }
-      }
-      __syncthreads();
-      if (tid < J) {
-        const int b = s.bin[tid];
-        if (p.out_trace) p.out_trace[((size_t)f * (p.depth + 1) + lvl) * J + tid] = b;
-        const double* g = gp + 3 * (tid * nbR + b);
-        const double X0 = g[0], X1 = g[1], X2 = g[2];
-        s.pose[tid][0] = X0; s.pose[tid][1] = X1; s.pose[tid][2] = X2;
-      }
-      __syncthreads();
-      cur = cur / (double)nR;
-    }
+    refine_levels<kRpsmThreads>(p, s, f, gp, eR, sv, bpR);
     if (tid < J) {
       double* o = p.out_pose + ((size_t)f * J + tid) * 3;
       o[0] = s.pose[tid][0]; o[1] = s.pose[tid][1]; o[2] = s.pose[tid][2];
     }
   }
+}
+
+// =================================================================================================
+// On-chip level 0 -- the B200-shaped path (pb200_rpsm picks it for offset-only pairwise tables with
+// shells within +-kRpsmEnumReach bins and n0 <= 16, i.e. every table built on the regular grid).
+//
+// One persistent 1024-thread block per SM; per frame
+//   * the heatmap coordinates of every (bin, view) are computed once (they do not depend on the
+//     joint) and parked in an L2-resident scratch of V*nb0*16 bytes per block;
+//   * the tree is walked depth-first by a small program built once per block (thread 0): every
+//     joint's unary is sampled exactly when it is first needed, from ITS V heatmaps staged in shared
+//     memory by the copy engine (cp.async.bulk + mbarrier; the next joint's maps -- or the next
+//     frame's first -- are requested as soon as the stage is free, so the copy runs under the
+//     max-product of the current joint);
+//   * energy vectors (nb0 float64 + their row / plane maxima) live in shared memory: with the
+//     first child's message folded into the parent's unary on the fly, the two reference skeletons
+//     never need more than 4 live vectors (128 KiB); deeper trees spill the extra ones to scratch;
+//   * the max over a parent's allowed children walks rows of n0 z-bins in ascending index order and
+//     skips every row (and every y-plane) whose maximum cannot beat the best value found so far --
+//     exact: a later candidate replaces the first maximum only if it is strictly larger;
+//   * parents whose accumulated energy is exactly 0 skip the maximisation (their product is 0); if
+//     back-tracking ever lands on such a bin (all-nonpositive energies) the frame is redone without
+//     the shortcut, so results are always those of np.argmax on the full product;
+//   * only the uint16 back pointers are written to global memory.
+// Bit-identical to rpsm_kernel (tests/test_gpu_rpsm.py compares both against the reference golden).
+// =================================================================================================
+#ifndef PB_RPSM_L2_HINTS
+#define PB_RPSM_L2_HINTS 1   // evict_first on the heatmap stream, evict_last on the parked coordinates
+#endif
+constexpr int kOcThreads = 1024;
+constexpr int kOcMaxPer = 4;                 // level-0 bins per thread: nb0 <= 4096
+constexpr int kOcMaxOps = 2 * kRpsmMaxJ;
+constexpr int kOcMaxUnits = kOcMaxPer * kOcThreads / 32;   // warp tasks of 32 consecutive parent bins
+constexpr int kOcStageBytes = 64 * 1024;
+constexpr int kOcSmemBudget = 227 * 1024;
+
+enum { kOpLeaf = 0, kOpFirst = 1, kOpAcc = 2 };
+struct OcOp {
+  uint8_t kind, joint, edge, src, dst, samp, pad0, pad1;
+};
+
+struct OcLayout {   // filled by the host (rpsm_onchip_layout)
+  int stage_off, stage_views;   // staged views per group; 0 = sample with __ldg (odd-sized / huge maps)
+  int dzm_off, dzm_cap;         // uint16 entries: allowed |dz| per (edge, |dy|, |dx|)
+  int refine_off;
+  int vec_off, vec_stride;      // vec_stride doubles per vector: nb0 + n0^2 (rounded up to even)
+  int nsm, nspill;              // vectors in shared memory / in scratch per block
+  size_t smem_bytes;
+  double* coords_ws;            // [blocks][V][nb0][2]
+  double* spill_ws;             // [blocks][nspill][vec_stride]
+  uint16_t* bp_ws;              // [blocks][E][nb0]
+};
+
+struct OcShared {
+  RpsmShared base;
+  OcOp ops[kOcMaxOps];
+  int nops, nsamp, root_buf, prog_err;
+  int reach[kRpsmMaxJ];
+  int doff[kRpsmMaxJ + 1];      // offset of edge e in the |dz| table
+  int contig[kRpsmMaxJ];        // 1: every |dz| set of the edge is one run (a spherical shell)
+  int child_start[kRpsmMaxJ + 1];
+  uint8_t child_edge[kRpsmMaxJ];
+  uint8_t samp_joint[kRpsmMaxJ];
+  uint8_t unit_order[kOcMaxUnits];
+  uint8_t pmask[kRpsmMaxJ * 8]; // refinement: allowed child bins (bit j) per (edge, parent bin)
+  unsigned long long mbar;
+  long long stage_tag;          // (frame, sample slot, group) of the bulk copy issued last; -1 = none
+  unsigned stage_seq;           // bulk-copy groups issued so far (mbarrier phase = stage_seq - 1)
+  int unit_next;                // next warp task of the running max-product
+  int nonfinite, redo, skip_ok;
+};
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_f64x2_hint(double* ptr, double a, double b, uint64_t pol) {
+#if PB_RPSM_L2_HINTS
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(ptr), "d"(a), "d"(b), "l"(pol) : "memory");
+#else
+  reinterpret_cast<double2*>(ptr)[0] = make_double2(a, b);
+#endif
+}
+__device__ __forceinline__ void ld_f64x2_hint(const double* ptr, double& a, double& b, uint64_t pol) {
+#if PB_RPSM_L2_HINTS
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(a), "=d"(b) : "l"(ptr), "l"(pol) : "memory");
+#else
+  const double2 v = reinterpret_cast<const double2*>(ptr)[0];
+  a = v.x; b = v.y;
+#endif
+}
+__device__ __forceinline__ void oc_mbar_init(uint32_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void oc_mbar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void oc_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "OCWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra OCDONE_%=;\n\t"
+      "bra OCWAIT_%=;\n\t"
+      "OCDONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void oc_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                            uint64_t pol) {
+#if PB_RPSM_L2_HINTS
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+#else
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+#endif
+}
+
+// Depth-first program (thread 0, once per block).  LEAF: dst = unary(joint).  FIRST: dst = unary(joint) *
+// msg(edge, src).  ACC: dst *= msg(edge, src).  Children in edge-array order, which is the order the
+// reference multiplies them in (pictorial.py:44-56).  Buffers are numbered so that the low ids (shared
+// memory) are reused first.  Also: child lists per joint (CSR) and the offsets of the |dz| table.
+__device__ void oc_build_program(OcShared& os, int J, int E, int root_idx, int nbuf) {
+  const RpsmShared& s = os.base;
+  struct Frame { int node, pos, acc, pending; };
+  Frame st[kRpsmMaxJ];
+  uint32_t free_mask = nbuf >= 32 ? 0xffffffffu : ((1u << nbuf) - 1u);
+  int sp = 0, nops = 0, nsamp = 0, ret = -1, err = 0;
+  st[sp++] = Frame{root_idx, 0, -1, -1};
+  auto alloc = [&]() -> int {
+    if (free_mask == 0u) { err = 1; return 0; }
+    const int b = __ffs(free_mask) - 1;
+    free_mask &= ~(1u << b);
+    return b;
+  };
+  while (sp > 0 && nops < kOcMaxOps - 1) {
+    Frame& fr = st[sp - 1];
+    if (ret >= 0) {   // a child has just returned its buffer
+      OcOp op;
+      op.joint = (uint8_t)fr.node; op.edge = (uint8_t)fr.pending; op.src = (uint8_t)ret;
+      op.samp = 0; op.pad0 = op.pad1 = 0;
+      if (fr.acc < 0) {
+        fr.acc = alloc();
+        op.kind = kOpFirst;
+        op.samp = (uint8_t)nsamp;
+        os.samp_joint[nsamp++] = (uint8_t)fr.node;
+      } else {
+        op.kind = kOpAcc;
+      }
+      op.dst = (uint8_t)fr.acc;
+      os.ops[nops++] = op;
+      free_mask |= 1u << ret;
+      ret = -1;
+    }
+    int e = fr.pos;
+    while (e < E && s.edge_p[e] != fr.node) ++e;
+    if (e < E) {
+      fr.pos = e + 1;
+      fr.pending = e;
+      if (sp >= kRpsmMaxJ) { err = 1; break; }
+      st[sp++] = Frame{s.edge_c[e], 0, -1, -1};
+      continue;
+    }
+    if (fr.acc < 0) {   // leaf
+      OcOp op;
+      op.kind = kOpLeaf; op.joint = (uint8_t)fr.node; op.edge = 0; op.src = 0; op.pad0 = op.pad1 = 0;
+      op.dst = (uint8_t)alloc();
+      op.samp = (uint8_t)nsamp;
+      os.samp_joint[nsamp++] = (uint8_t)fr.node;
+      os.ops[nops++] = op;
+      ret = op.dst;
+    } else {
+      ret = fr.acc;
+    }
+    --sp;
+  }
+  if (sp != 0 || nsamp != J) err = 1;   // not a tree spanning all joints
+  os.nops = nops;
+  os.nsamp = nsamp;
+  os.root_buf = ret < 0 ? 0 : ret;
+  os.prog_err = err;
+  int off = 0, ce = 0;
+  for (int e = 0; e < E; ++e) {
+    os.doff[e] = off;
+    off += (os.reach[e] + 1) * (2 * os.reach[e] + 1);   // rows |oy| = 0..r, columns ox = -r..r
+  }
+  os.doff[E] = off;
+  for (int j = 0; j < J; ++j) {
+    os.child_start[j] = ce;
+    for (int e = 0; e < E; ++e)
+      if (s.edge_p[e] == j) os.child_edge[ce++] = (uint8_t)e;
+  }
+  os.child_start[J] = ce;
+}
+
+// ---- refinement levels for 2^3 grids (the reference's RECUR_NBINS = 2), block-wide ------------------
+// Same arithmetic as refine_levels, arranged for 1024 threads: the limb predicates of all E x 8 x 8 (parent
+// bin, child bin) pairs do not depend on the energies, so they are evaluated one per thread next to the
+// heatmap samples; what is left for warp 0 is a table-driven max-product over 8-bin vectors.
+template <int T>
+__device__ __forceinline__ void refine_levels8(const RpsmParams& p, OcShared& os, int f, double* gp,
+                                               double* eR, double* sv, uint8_t* bpR) {
+  RpsmShared& s = os.base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int J = p.J, E = J - 1, V = p.V;
+  double cur = p.grid_size / (double)p.n0;
+  for (int lvl = 1; lvl <= p.depth; ++lvl) {
+    for (int t = tid; t < J * 8; t += T) {
+      const int j = t >> 3, b = t & 7;
+      double X[3];
+      bin_to_point(cur, 2, b, s.pose[j], X);
+      gp[3 * t] = X[0]; gp[3 * t + 1] = X[1]; gp[3 * t + 2] = X[2];
+    }
+    __syncthreads();
+    for (int t = tid; t < V * J * 8; t += T) {
+      const int v = t / (J * 8), r = t - v * (J * 8);
+      sv[t] = sample_view(p, s, f, v, r >> 3, gp + 3 * r);
+    }
+    for (int t = tid; t < E * 64; t += T) {   // E * 64 is a multiple of 32: whole warps
+      const int e = t >> 6, i = (t >> 3) & 7, jj = t & 7;
+      const double* gi = gp + 3 * (s.edge_p[e] * 8 + i);
+      const double* gj = gp + 3 * (s.edge_c[e] * 8 + jj);
+      const double dx = gi[0] - gj[0], dy = gi[1] - gj[1], dz = gi[2] - gj[2];
+      const double d = sqrt((dx * dx + dy * dy) + dz * dz);
+      const unsigned bal = __ballot_sync(0xffffffffu, fabs(d - s.limb[e]) <= p.tol);
+      if (jj == 0) os.pmask[e * 8 + i] = (uint8_t)((bal >> (lane & 24)) & 0xffu);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int t = lane; t < J * 8; t += 32) {
+        double u = 0.0;
+        for (int v = 0; v < V; ++v) u = u + sv[v * (J * 8) + t];
+        eR[t] = u;
+      }
+      __syncwarp();
+      const int i = lane >> 2, q = lane & 3;   // lanes = (parent bin i) x (child bins 2q, 2q+1)
+      for (int oi = 0; oi < J; ++oi) {
+        const int par = s.order[oi];
+        const int c0 = os.child_start[par], c1 = os.child_start[par + 1];
+        if (c0 == c1) continue;
+        double acc = eR[par * 8 + i];
+        for (int ce = c0; ce < c1; ++ce) {
+          const int e = os.child_edge[ce], c = s.edge_c[e];
+          const unsigned pm = os.pmask[e * 8 + i];
+          double best = 0.0;
+          int bidx = -1;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int jj = 2 * q + h;
+            const double val = ((pm >> jj) & 1u) ? eR[c * 8 + jj] : 0.0;
+            if (bidx < 0 || val > best) { best = val; bidx = jj; }
+          }
+#pragma unroll
+          for (int o = 1; o <= 2; o <<= 1) {  // merge the 4 lanes of this parent bin
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ob = __shfl_xor_sync(0xffffffffu, bidx, o);
+            if (ov > best || (ov == best && ob < bidx)) { best = ov; bidx = ob; }
+          }
+          acc = acc * best;
+          if (q == 0) bpR[e * 8 + i] = (uint8_t)bidx;
+        }
+        __syncwarp();
+        if (q == 0) eR[par * 8 + i] = acc;
+        __syncwarp();
+      }
+      if (lane == 0) {
+        const double* er = eR + p.root_idx * 8;
+        double best = er[0];
+        int bidx = 0;
+        for (int b = 1; b < 8; ++b)
+          if (er[b] > best) { best = er[b]; bidx = b; }
+        s.bin[p.root_idx] = bidx;
+        for (int oi = J - 1; oi >= 0; --oi) {
+          const int par = s.order[oi];
+          for (int ce = os.child_start[par]; ce < os.child_start[par + 1]; ++ce) {
+            const int e = os.child_edge[ce];
+            s.bin[s.edge_c[e]] = bpR[e * 8 + s.bin[par]];
+          }
+        }
+      }
+      __syncwarp();
+      if (lane < J) {
+        const int b = s.bin[lane];
+        if (p.out_trace) p.out_trace[((size_t)f * (p.depth + 1) + lvl) * J + lane] = b;
+        const double* g = gp + 3 * (lane * 8 + b);
+        const double X0 = g[0], X1 = g[1], X2 = g[2];
+        s.pose[lane][0] = X0; s.pose[lane][1] = X1; s.pose[lane][2] = X2;
+      }
+    }
+    __syncthreads();
+    cur = cur / 2.0;
+  }
+}
+
+// What the reference's product with the 0/1 matrix does once the first maximum over the ALLOWED children
+// is known (`found`, value `best`): disallowed children are candidates with value 0 at their own index.
+__device__ __forceinline__ void oc_finish_max(const uint32_t* __restrict__ row0, int n0, int nb0, int iy, int ix,
+                                              int iz, int found, double best, double& val, int& arg) {
+  const double mA = found >= 0 ? best : 0.0;
+  if (found >= 0 && mA > 0.0) {
+    val = mA;
+    arg = found;
+    return;
+  }
+  int first_dis = -1;   // rare path: every allowed energy is <= 0
+  for (int j = 0; j < nb0; ++j) {
+    int jy, jx, jz;
+    bin_coords(n0, j, jy, jx, jz);
+    const int d = (abs(iy - jy) * n0 + abs(ix - jx)) * n0 + abs(iz - jz);
+    if (!((__ldg(row0 + (d >> 5)) >> (d & 31)) & 1u)) { first_dis = j; break; }
+  }
+  if (found < 0) { val = 0.0; arg = 0; }
+  else if (mA == 0.0) { val = 0.0; arg = (first_dis >= 0 && first_dis < found) ? first_dis : found; }
+  else if (first_dis >= 0) { val = 0.0; arg = first_dis; }
+  else { val = mA; arg = found; }
+}
+
+// ---- shared-memory accessors by 32-bit address (keeps the hot loops free of generic-pointer arithmetic) ----
+__device__ __forceinline__ double oc_lds64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void oc_sts64(uint32_t a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ unsigned oc_lds16(uint32_t a) {
+  unsigned v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+// One candidate child at shared address `a`: it becomes the running first maximum iff k is inside the
+// lane's range and its energy is STRICTLY larger (children are visited in ascending index order).
+__device__ __forceinline__ void oc_cand_ge(uint32_t a, int k, int lo, double& best, uint32_t& fa) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .f64 v;\n\t"
+      "ld.shared.f64 v, [%2];\n\t"
+      "setp.ge.s32 q, %3, %4;\n\t"
+      "setp.gt.and.f64 p, v, %0, q;\n\t"
+      "selp.f64 %0, v, %0, p;\n\t"
+      "selp.b32 %1, %2, %1, p;\n\t"
+      "}" : "+d"(best), "+r"(fa) : "r"(a), "r"(k), "r"(lo) : "memory");
+}
+__device__ __forceinline__ void oc_cand_le(uint32_t a, int k, int hi, double& best, uint32_t& fa) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .f64 v;\n\t"
+      "ld.shared.f64 v, [%2];\n\t"
+      "setp.le.s32 q, %3, %4;\n\t"
+      "setp.gt.and.f64 p, v, %0, q;\n\t"
+      "selp.f64 %0, v, %0, p;\n\t"
+      "selp.b32 %1, %2, %1, p;\n\t"
+      "}" : "+d"(best), "+r"(fa) : "r"(a), "r"(k), "r"(hi) : "memory");
+}
+
+// One warp task of the max-product: the 32 consecutive parent bins [32u, 32u+32) of edge e.
+//   D[i] <- D[i] * max_j ( P[i,j] ? S[j] : 0 ),  bp[i] <- first argmax           (pictorial.py:50-56)
+// FAST FORM (source and destination in shared memory, every |dz| set of the edge one run, finite frame):
+// children are visited by OFFSET (oy, ox, k), the same for every lane, in ascending child index, so all
+// lanes run the same loops and differ only in predicates -- the warp never diverges.  A row of children is
+// skipped when no lane can still be improved by it (row maxima RS); lanes that cannot be improved, or whose
+// row lies outside the grid, load from a harmless address inside the block's shared memory and are masked
+// by their k-range.  sS / sD: shared addresses of the vectors; sDz: the edge's |dz| table
+// [(r+1)][2r+1] uint16 (bit k = |dz| = k allowed), indexed by (|oy|, ox + r).
+__device__ __forceinline__ bool oc_maxprod_unit_smem(uint32_t sS, uint32_t sD, uint16_t* __restrict__ bp_e,
+                                                     uint32_t sDz, const uint32_t* __restrict__ row0, int n0,
+                                                     int nb0, int r, int u, bool skip_ok) {
+  const int lane = threadIdx.x & 31;
+  const int i = 32 * u + lane;
+  const bool valid = i < nb0;
+  const int iz = i % n0, qi = i / n0, ix = qi % n0, iy = qi / n0;
+  const double acc = valid ? oc_lds64(sD + (uint32_t)i * 8u) : 0.0;
+  const bool skip = valid && skip_ok && acc == 0.0;   // 0 * (finite max) = 0: argmax resolved only if ever needed
+  const bool active = valid && !skip;
+  const uint32_t sRS = sS + (uint32_t)nb0 * 8u;       // max of every row of n0 z-bins of the source
+  double best = -INFINITY;
+  uint32_t fa = 0u;                                   // shared address of the running first maximum
+  if (__any_sync(0xffffffffu, active)) {
+    const int w = 2 * r + 1;
+    const int klo = -iz, khi = n0 - 1 - iz;
+    const uint32_t own = sS + (uint32_t)(valid ? i : 0) * 8u;
+    for (int oy = -r; oy <= r; ++oy) {
+      const bool yok = active && (unsigned)(iy + oy) < (unsigned)n0;
+      if (!__any_sync(0xffffffffu, yok)) continue;
+      uint32_t dza = sDz + (uint32_t)(abs(oy) * w) * 2u;
+      int rowq = qi + oy * n0 - r;                    // child row of this lane for ox = -r
+      for (int ox = -r; ox <= r; ++ox, dza += 2u, ++rowq) {
+        const unsigned dm = oc_lds16(dza);            // same for every lane
+        if (dm == 0u) continue;
+        const bool inrow = yok && (unsigned)(ix + ox) < (unsigned)n0;
+        double rsv = -INFINITY;
+        if (inrow) rsv = oc_lds64(sRS + (uint32_t)rowq * 8u);
+        const bool rowok = rsv > best;
+        if (!__any_sync(0xffffffffu, rowok)) continue;
+        const int a = __ffs(dm) - 1, b = 31 - __clz(dm);
+        const int lo = rowok ? klo : 64, hi = rowok ? khi : -64;
+        const uint32_t base = rowok ? sS + (uint32_t)(rowq * n0 + iz) * 8u : own;
+        for (int k = -b; k <= -a; ++k) oc_cand_ge(base + (uint32_t)(k * 8), k, lo, best, fa);   // below the parent's z
+        for (int k = a > 0 ? a : 1; k <= b; ++k) oc_cand_le(base + (uint32_t)(k * 8), k, hi, best, fa);   // above
+      }
+    }
+  }
+  bool bad = false;
+  if (active) {
+    const int found = fa != 0u ? (int)((fa - sS) >> 3) : -1;
+    double val;
+    int arg;
+    oc_finish_max(row0, n0, nb0, iy, ix, iz, found, best, val, arg);
+    const double out = acc * val;
+    bad = !(fabs(out) <= 1.79769313486231570e308);
+    oc_sts64(sD + (uint32_t)i * 8u, out);
+    bp_e[i] = (uint16_t)arg;
+  } else if (skip) {
+    oc_sts64(sD + (uint32_t)i * 8u, 0.0);
+    bp_e[i] = (uint16_t)0xffff;
+  }
+  return bad;
+}
+
+// EXACT PER-LANE FORM (vectors spilled to scratch, |dz| sets with gaps, or non-finite energies): every lane
+// enumerates its own allowed children with the reference's first-candidate rule.
+__device__ __forceinline__ bool oc_maxprod_unit_exact(const double* S, double* D, uint16_t* __restrict__ bp_e,
+                                                      const uint16_t* __restrict__ dz, const uint32_t* __restrict__ row0,
+                                                      int n0, int nb0, int r, int u, bool skip_ok) {
+  const int lane = threadIdx.x & 31;
+  const int i = 32 * u + lane;
+  if (i >= nb0) return false;
+  const int iz = i % n0, qi = i / n0, ix = qi % n0, iy = qi / n0;
+  const double acc = D[i];
+  if (skip_ok && acc == 0.0) {
+    D[i] = 0.0;
+    bp_e[i] = (uint16_t)0xffff;
+    return false;
+  }
+  const double* RS = S + nb0;
+  const int w = 2 * r + 1;
+  int found = -1;
+  double best = 0.0;
+  const int jy1 = min(iy + r, n0 - 1), jx0 = max(ix - r, 0), jx1 = min(ix + r, n0 - 1);
+  for (int jy = max(iy - r, 0); jy <= jy1; ++jy)
+    for (int jx = jx0; jx <= jx1; ++jx) {
+      const int row = jy * n0 + jx;
+      if (found >= 0 && !(RS[row] > best)) continue;
+      const unsigned dm = dz[abs(iy - jy) * w + (jx - ix) + r];
+      const int base = row * n0;
+      for (int jz = 0; jz < n0; ++jz)
+        if ((dm >> abs(iz - jz)) & 1u) {
+          const double v = S[base + jz];
+          if (found < 0 || v > best) { best = v; found = base + jz; }
+        }
+    }
+  double val;
+  int arg;
+  oc_finish_max(row0, n0, nb0, iy, ix, iz, found, best, val, arg);
+  const double out = acc * val;
+  D[i] = out;
+  bp_e[i] = (uint16_t)arg;
+  return !(fabs(out) <= 1.79769313486231570e308);
+}
+
+__global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmParams p, const OcLayout L) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  OcShared& os = *reinterpret_cast<OcShared*>(smem_raw);
+  RpsmShared& s = os.base;
+  constexpr int T = kOcThreads;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = p.n0, nb0 = n0 * n0 * n0, words0 = (nb0 + 31) / 32;
+  const int J = p.J, E = J - 1, V = p.V;
+  const int HWm = p.H * p.W;
+  const int nbR_ = p.nR * p.nR * p.nR;
+  const int nunits = (nb0 + 31) / 32;
+  float* stage = reinterpret_cast<float*>(smem_raw + L.stage_off);
+  uint16_t* dzm = reinterpret_cast<uint16_t*>(smem_raw + L.dzm_off);
+  double* vec_sm = reinterpret_cast<double*>(smem_raw + L.vec_off);
+  double* gp = reinterpret_cast<double*>(smem_raw + L.refine_off);
+  double* eR = gp + (size_t)J * nbR_ * 3;
+  double* sv = eR + (size_t)J * nbR_;
+  uint8_t* bpR = reinterpret_cast<uint8_t*>(sv + (size_t)V * J * nbR_);
+  double* coords = L.coords_ws + (size_t)blockIdx.x * V * nb0 * 2;
+  double* spill = L.spill_ws + (size_t)blockIdx.x * L.nspill * L.vec_stride;
+  uint16_t* bp = L.bp_ws + (size_t)blockIdx.x * E * nb0;
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&os.mbar);
+  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+  const uint32_t vec_s = (uint32_t)__cvta_generic_to_shared(vec_sm);
+  const uint32_t dzm_s = (uint32_t)__cvta_generic_to_shared(dzm);
+  const uint64_t pol_keep = l2_policy_evict_last();
+  const uint64_t pol_stream = l2_policy_evict_first();
+  auto vec = [&](int b) -> double* {
+    return b < L.nsm ? vec_sm + (size_t)b * L.vec_stride : spill + (size_t)(b - L.nsm) * L.vec_stride;
+  };
+
+  // ---- once per block: tree program, shell reach and |dz| sets of every edge, task order -------------
+  if (tid < E) { s.edge_p[tid] = p.edges[2 * tid]; s.edge_c[tid] = p.edges[2 * tid + 1]; }
+  if (tid < J) s.order[tid] = p.order[tid];
+  if (tid < kRpsmMaxJ) { os.reach[tid] = 0; os.contig[tid] = 1; }
+  if (tid == 0) {
+    os.stage_tag = -1;
+    os.stage_seq = 0;
+    oc_mbar_init(mbar);
+  }
+  __syncthreads();
+  for (int t = tid; t < E * nb0; t += T) {
+    const int e = t / nb0, d = t - e * nb0;
+    const uint32_t* row0 = p.pair_bits + (size_t)e * nb0 * words0;
+    if ((__ldg(row0 + (d >> 5)) >> (d & 31)) & 1u) {
+      int dy, dx, dz;
+      bin_coords(n0, d, dy, dx, dz);
+      atomicMax(&os.reach[e], max(dy, max(dx, dz)));
+    }
+  }
+  __syncthreads();
+  if (tid == 0) oc_build_program(os, J, E, p.root_idx, L.nsm + L.nspill);
+  __syncthreads();
+  if (os.prog_err || os.doff[E] > L.dzm_cap) __trap();   // the host sizes both; cannot happen for a tree
+  for (int t = tid; t < os.doff[E]; t += T) {
+    int e = 0;
+    while (t >= os.doff[e + 1]) ++e;
+    const int w = 2 * os.reach[e] + 1, local = t - os.doff[e];
+    const int adx = abs(local % w - os.reach[e]), ady = local / w;
+    const uint32_t* row0 = p.pair_bits + (size_t)e * nb0 * words0;
+    uint32_t m = 0u;
+    for (int dz = 0; dz < n0; ++dz) {
+      const int d = (ady * n0 + adx) * n0 + dz;
+      m |= ((__ldg(row0 + (d >> 5)) >> (d & 31)) & 1u) << dz;
+    }
+    dzm[t] = (uint16_t)m;
+    if (m != 0u) {
+      const uint32_t run = m >> (__ffs(m) - 1);
+      if ((run & (run + 1u)) != 0u) os.contig[e] = 0;   // more than one run of allowed |dz|
+    }
+  }
+  // warp tasks sorted by how much of their neighbourhood lies inside the grid (interior first): the
+  // dynamic hand-out below then finishes all warps together
+  for (int u = tid; u < nunits; u += T) {
+    auto key = [&](int w) {
+      const int q = (32 * w + 16) / n0, cx = q % n0, cy = q / n0;
+      return abs(2 * cx - (n0 - 1)) + abs(2 * cy - (n0 - 1));
+    };
+    const int ku = key(u);
+    int rank = 0;
+    for (int w = 0; w < nunits; ++w) {
+      const int kw = key(w);
+      rank += (kw < ku) || (kw == ku && w < u);
+    }
+    os.unit_order[rank] = (uint8_t)u;
+  }
+  __syncthreads();
+
+  const int ngroups = L.stage_views > 0 ? (V + L.stage_views - 1) / L.stage_views : 0;
+  // thread 0: hand group g of sampling slot si of frame fr to the copy engine
+  auto stage_issue = [&](int fr, int si, int g) {
+    const int j = os.samp_joint[si];
+    const int v0 = g * L.stage_views, nv = min(V - v0, L.stage_views);
+    oc_mbar_expect(mbar, (uint32_t)(nv * HWm * 4));
+    for (int v = 0; v < nv; ++v)
+      oc_bulk_g2s(stage_s + (uint32_t)(v * HWm * 4),
+                  p.hm + (((size_t)fr * V + (v0 + v)) * J + j) * (size_t)HWm, (uint32_t)(HWm * 4), mbar, pol_stream);
+    os.stage_tag = ((long long)fr << 16) | ((long long)si << 8) | (long long)g;
+    os.stage_seq += 1;
+  };
+  // all threads: wait until group g of slot si of frame fr is in the stage
+  auto stage_acquire = [&](int fr, int si, int g) {
+    const long long tag = ((long long)fr << 16) | ((long long)si << 8) | (long long)g;
+    if (os.stage_tag != tag) {   // block-uniform: cold start, or a redo pass
+      if (os.stage_seq > 0) oc_mbar_wait(mbar, (os.stage_seq - 1) & 1u);   // drain the copy in flight
+      __syncthreads();
+      if (tid == 0) stage_issue(fr, si, g);
+      __syncthreads();
+    }
+    oc_mbar_wait(mbar, (os.stage_seq - 1) & 1u);
+  };
+
+  for (int f = blockIdx.x; f < p.B; f += gridDim.x) {
+    __syncthreads();
+    if (tid < V) {
+      load_cam(p.campack + (size_t)p.cam_index[(size_t)f * V + tid] * PB200_CAM_STRIDE, s.cam[tid]);
+      for (int k = 0; k < 6; ++k) s.aff[tid][k] = p.box_affine[((size_t)f * V + tid) * 6 + k];
+    }
+    if (tid < E) s.limb[tid] = p.limb[(size_t)f * E + tid];
+    if (tid == 0) { os.nonfinite = 0; os.skip_ok = 1; os.redo = 0; }
+    __syncthreads();
+    const double centre[3] = {p.root[3 * (size_t)f], p.root[3 * (size_t)f + 1], p.root[3 * (size_t)f + 2]};
+
+    // ---- heatmap coordinates of every (bin, view), once per frame ---------------------------------
+    for (int b = tid; b < nb0; b += T) {
+      double X[3];
+      bin_to_point(p.grid_size, n0, b, centre, X);
+      for (int v = 0; v < V; ++v) {
+        double hx, hy;
+        grid_to_heatmap(s.cam[v], s.aff[v], X, p.W, p.H, p.img_w, p.img_h, hx, hy);
+        st_f64x2_hint(coords + ((size_t)v * nb0 + b) * 2, hx, hy, pol_keep);
+      }
+    }
+    // (every thread reads back only the coordinates it wrote itself: no barrier needed)
+
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int oi = 0; oi < os.nops; ++oi) {
+        const OcOp op = os.ops[oi];
+        double* D = vec(op.dst);
+        if (op.kind != kOpAcc) {   // sample the unary of op.joint: float64 sum over views, in order
+          double u[kOcMaxPer];
+#pragma unroll
+          for (int k = 0; k < kOcMaxPer; ++k) u[k] = 0.0;
+          const int W = p.W;
+          if (ngroups > 0) {
+            for (int g = 0; g < ngroups; ++g) {
+              stage_acquire(f, op.samp, g);
+              const int v0 = g * L.stage_views, v1 = min(V, v0 + L.stage_views);
+#pragma unroll
+              for (int k = 0; k < kOcMaxPer; ++k) {
+                const int b = tid + k * T;
+                if (b < nb0)
+                  for (int v = v0; v < v1; ++v) {
+                    double hx, hy;
+                    ld_f64x2_hint(coords + ((size_t)v * nb0 + b) * 2, hx, hy, pol_keep);
+                    const float* m = stage + (size_t)(v - v0) * HWm;
+                    u[k] = u[k] + bilinear_zero_outside([m, W](int y, int x) { return m[y * W + x]; }, p.W, p.H, hx, hy);
+                  }
+              }
+              __syncthreads();   // every thread is done with the stage
+              if (tid == 0) {    // request what is needed next: it lands under the max-product below
+                if (g + 1 < ngroups) stage_issue(f, op.samp, g + 1);
+                else if (op.samp + 1 < os.nsamp) stage_issue(f, op.samp + 1, 0);
+                else if (f + (int)gridDim.x < p.B) stage_issue(f + (int)gridDim.x, 0, 0);
+              }
+              if (g + 1 < ngroups) __syncthreads();
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < kOcMaxPer; ++k) {
+              const int b = tid + k * T;
+              if (b < nb0)
+                for (int v = 0; v < V; ++v) {
+                  double hx, hy;
+                  ld_f64x2_hint(coords + ((size_t)v * nb0 + b) * 2, hx, hy, pol_keep);
+                  const float* m = p.hm + (((size_t)f * V + v) * J + op.joint) * (size_t)HWm;
+                  u[k] = u[k] + bilinear_zero_outside([m, W](int y, int x) { return __ldg(m + y * W + x); }, p.W, p.H, hx, hy);
+                }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < kOcMaxPer; ++k) {
+            const int b = tid + k * T;
+            if (b < nb0) {
+              if (!(fabs(u[k]) <= 1.79769313486231570e308)) os.nonfinite = 1;   // inf / NaN: no shortcuts
+              D[b] = u[k];
+            }
+          }
+        }
+        if (op.kind != kOpLeaf) {
+          double* S = vec(op.src);
+          for (int r = tid; r < n0 * n0; r += T) {   // max of every row of n0 z-bins of the source
+            double m = -INFINITY;
+            for (int z = 0; z < n0; ++z) {
+              const double v = S[r * n0 + z];
+              if (v > m) m = v;
+            }
+            S[nb0 + r] = m;
+          }
+          if (tid == 0) os.unit_next = 0;
+          __syncthreads();
+          const int e = op.edge;
+          const bool finite = os.nonfinite == 0;
+          const bool uniform = finite && os.contig[e] != 0;
+          const bool skip_ok = pass == 0 && os.skip_ok != 0 && finite;
+          const uint32_t* row0 = p.pair_bits + (size_t)e * nb0 * words0;
+          bool bad = false;
+          for (;;) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&os.unit_next, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= nunits) break;
+            const int u = os.unit_order[t];
+            if (uniform && op.src < L.nsm && op.dst < L.nsm)   // the fast form: everything on chip
+              bad |= oc_maxprod_unit_smem(vec_s + (uint32_t)((size_t)op.src * L.vec_stride * 8),
+                                          vec_s + (uint32_t)((size_t)op.dst * L.vec_stride * 8), bp + (size_t)e * nb0,
+                                          dzm_s + (uint32_t)os.doff[e] * 2u, row0, n0, nb0, os.reach[e], u, skip_ok);
+            else
+              bad |= oc_maxprod_unit_exact(S, D, bp + (size_t)e * nb0, dzm + os.doff[e], row0, n0, nb0, os.reach[e],
+                                           u, skip_ok);
+          }
+          if (bad) os.nonfinite = 1;
+        }
+        __syncthreads();
+      }
+
+      // ---- root argmax (first maximum) and back-tracking ----------------------------------------
+      {
+        const double* er = vec(os.root_buf);
+        double best = -INFINITY;
+        int bidx = 0x7fffffff;
+        for (int b = tid; b < nb0; b += T) {
+          const double v = er[b];
+          if (bidx == 0x7fffffff || v > best) { best = v; bidx = b; }
+        }
+        warp_first_max(best, bidx);
+        if (lane == 0) { s.red_val[warp] = best; s.red_idx[warp] = bidx; }
+        __syncthreads();
+        if (tid == 0) {
+          for (int w = 1; w < T / 32; ++w)
+            if (s.red_val[w] > best || (s.red_val[w] == best && s.red_idx[w] < bidx)) {
+              best = s.red_val[w];
+              bidx = s.red_idx[w];
+            }
+          s.bin[p.root_idx] = bidx;
+          int redo = 0;
+          for (int oi = J - 1; oi >= 0; --oi) {   // parents before children
+            const int par = s.order[oi];
+            for (int ce = os.child_start[par]; ce < os.child_start[par + 1]; ++ce) {
+              const int e = os.child_edge[ce];
+              int b = bp[(size_t)e * nb0 + s.bin[par]];
+              if (b == 0xffff) { redo = 1; b = 0; }
+              s.bin[s.edge_c[e]] = b;
+            }
+          }
+          os.redo = redo;
+        }
+        __syncthreads();
+      }
+      if (!os.redo) break;   // block-uniform
+    }
+
+    if (tid < J) {
+      double X[3];
+      bin_to_point(p.grid_size, n0, s.bin[tid], centre, X);
+      s.pose[tid][0] = X[0]; s.pose[tid][1] = X[1]; s.pose[tid][2] = X[2];
+      if (p.out_trace) p.out_trace[((size_t)f * (p.depth + 1)) * J + tid] = s.bin[tid];
+    }
+    __syncthreads();
+    if (p.nR == 2) refine_levels8<T>(p, os, f, gp, eR, sv, bpR);
+    else refine_levels<T>(p, s, f, gp, eR, sv, bpR);
+    if (tid < J) {
+      double* o = p.out_pose + ((size_t)f * J + tid) * 3;
+      o[0] = s.pose[tid][0]; o[1] = s.pose[tid][1]; o[2] = s.pose[tid][2];
+    }
+  }
+  // every bulk copy that was issued has been waited for: stage_issue only looks ahead to frames this
+  // block will process, and stage_acquire waits for each before its data is read
 }
 
 // P[e][i][j] = | |g_i - g_j| - L_e | < 0.4 L_e on the zero-centred n^3 grid
@@ -549,6 +1312,18 @@ __global__ void pairwise_lut_check_kernel(const uint32_t* __restrict__ bits, int
     bad |= ((m >> k) & 1u) != want;
   }
   if (bad) atomicOr(flag, 1);
+  // flag[1] = largest |index offset| of an allowed pair in row 0 of any edge (the shell "reach")
+  if (i == 0 && m != 0u) {
+    int r = 0;
+    for (int k = 0; k < 32; ++k) {
+      const int j = w * 32 + k;
+      if (j >= nb || !((m >> k) & 1u)) continue;
+      int jy, jx, jz;
+      bin_coords(n, j, jy, jx, jz);
+      r = max(r, max(jy, max(jx, jz)));
+    }
+    atomicMax(flag + 1, r);
+  }
 }
 
 static int next_pow2(int n) {
@@ -571,6 +1346,52 @@ static int rpsm_slots(int B, int n_sm) {
   return B < cap ? (B > 0 ? B : 1) : cap;
 }
 
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// live energy vectors the depth-first program can need for ANY tree of J joints: one accumulator per
+// ancestor with a second child pending (each costs the tree two more nodes) + source + destination
+static int onchip_max_vectors(int J) { return (J - 1) / 2 + 2; }
+
+static size_t onchip_workspace_bytes(int blocks, int V, int J, int nb0, int n0, int nspill) {
+  const size_t vec_stride = align_up((size_t)nb0 + (size_t)n0 * n0, 2);
+  size_t b = align_up((size_t)blocks * V * nb0 * 2 * sizeof(double), 256);
+  b += align_up((size_t)blocks * nspill * vec_stride * sizeof(double), 256);
+  b += align_up((size_t)blocks * (J - 1) * nb0 * sizeof(uint16_t), 256);
+  return b;
+}
+
+// Shared-memory plan of rpsm_onchip_kernel; returns false when the shape does not fit the on-chip path.
+static bool rpsm_onchip_layout(const float* hm, int V, int J, int H, int W, int n0, int nbR, int max_reach,
+                               OcLayout& L) {
+  const int nb0 = n0 * n0 * n0, E = J - 1;
+  if (n0 > 16 || nb0 > kOcMaxPer * kOcThreads || max_reach < 0 || max_reach > kRpsmEnumReach) return false;
+  const size_t map_bytes = (size_t)H * W * 4;
+  size_t off = align_up(sizeof(OcShared), 128);
+  L.stage_views = 0;
+  if ((H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(hm) & 15u) == 0 && map_bytes <= (size_t)kOcStageBytes) {
+    L.stage_views = (int)((size_t)kOcStageBytes / map_bytes);
+    if (L.stage_views > V) L.stage_views = V;
+  }
+  L.stage_off = (int)off;
+  off = align_up(off + (size_t)L.stage_views * map_bytes, 128);
+  L.dzm_off = (int)off;
+  L.dzm_cap = E * (max_reach + 1) * (2 * max_reach + 1);
+  off = align_up(off + (size_t)L.dzm_cap * sizeof(uint16_t), 16);
+  L.refine_off = (int)off;
+  off = align_up(off + (size_t)J * nbR * (3 + 1 + V) * sizeof(double) + (size_t)E * nbR, 16);
+  L.vec_off = (int)off;
+  L.vec_stride = (int)align_up((size_t)nb0 + (size_t)n0 * n0, 2);
+  const size_t vec_bytes = (size_t)L.vec_stride * sizeof(double);
+  if (off + 2 * vec_bytes > (size_t)kOcSmemBudget) return false;   // source + destination must be on chip
+  const int need = onchip_max_vectors(J);
+  int nsm = (int)(((size_t)kOcSmemBudget - off) / vec_bytes);
+  if (nsm > need) nsm = need;
+  L.nsm = nsm;
+  L.nspill = need - nsm;
+  L.smem_bytes = off + (size_t)nsm * vec_bytes;
+  return true;
+}
+
 }  // namespace pb200
 
 using namespace pb200;
@@ -580,14 +1401,18 @@ extern "C" size_t pb200_rpsm_workspace_bytes(int B, int J, int first_nbins, int 
   const size_t nb0 = (size_t)first_nbins * first_nbins * first_nbins;
   const size_t slots = (size_t)rpsm_slots(B, n_sm);
   const size_t e_bytes = ((slots * J * nb0 * sizeof(double) + 255) / 256) * 256;
-  return e_bytes + slots * (size_t)(J - 1) * nb0 * sizeof(uint16_t);
+  const size_t generic = e_bytes + slots * (size_t)(J - 1) * nb0 * sizeof(uint16_t);
+  // the on-chip path: one block per SM, coordinates for up to PB200_MAX_VIEWS views, every vector spilled
+  const size_t onchip = onchip_workspace_bytes(B < n_sm ? B : n_sm, PB200_MAX_VIEWS, J, (int)nb0, first_nbins,
+                                               onchip_max_vectors(J));
+  return generic > onchip ? generic : onchip;
 }
 
 extern "C" int pb200_rpsm(const float* hm, int B, int V, int J, int H, int W, const double* campack,
                           const int32_t* cam_index, const double* box_affine, int img_w, int img_h,
                           const double* root, const double* limb, const int32_t* edges,
                           const int32_t* order, int root_idx, const uint32_t* pair_bits, int use_lut,
-                          int first_nbins, int recur_nbins, int recur_depth, double grid_size,
+                          int max_reach, int first_nbins, int recur_nbins, int recur_depth, double grid_size,
                           double tolerance, void* workspace, size_t workspace_bytes,
                           double* out_pose, int32_t* out_trace, void* stream) {
   PB_REQUIRE(B >= 0 && H >= 2 && W >= 2, "bad shape B=%d H=%d W=%d", B, H, W);
@@ -603,15 +1428,13 @@ extern "C" int pb200_rpsm(const float* hm, int B, int V, int J, int H, int W, co
   PB_REQUIRE(recur_nbins >= 1 && recur_nbins * recur_nbins * recur_nbins <= kRpsmMaxBinsR,
              "recur_nbins^3 must be <= %d", kRpsmMaxBinsR);
   PB_REQUIRE(recur_depth >= 0, "recur_depth < 0");
+  PB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
   const int sm = cached_sm_count();
   if (sm <= 0) return PB200_ERR_CUDA;
   const int nb0 = first_nbins * first_nbins * first_nbins;
+  const int nbR = recur_nbins * recur_nbins * recur_nbins;
   PB_REQUIRE(workspace_bytes >= pb200_rpsm_workspace_bytes(B, J, first_nbins, sm),
              "workspace too small: %zu < %zu", workspace_bytes, pb200_rpsm_workspace_bytes(B, J, first_nbins, sm));
-  const size_t smem = rpsm_smem_bytes(nb0, J, V, recur_nbins * recur_nbins * recur_nbins);
-  PB_REQUIRE(smem <= 227 * 1024, "first_nbins=%d needs %zu bytes of shared memory", first_nbins, smem);
-  PB_CUDA(cudaFuncSetAttribute(rpsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int slots = rpsm_slots(B, sm);
   RpsmParams p;
   p.hm = hm; p.B = B; p.V = V; p.J = J; p.H = H; p.W = W;
   p.campack = campack; p.cam_index = cam_index; p.box_affine = box_affine;
@@ -620,10 +1443,45 @@ extern "C" int pb200_rpsm(const float* hm, int B, int V, int J, int H, int W, co
   p.pair_bits = pair_bits; p.use_lut = use_lut;
   p.n0 = first_nbins; p.nR = recur_nbins; p.depth = recur_depth; p.npad = next_pow2(nb0);
   p.grid_size = grid_size; p.tol = tolerance;
+  p.energy_ws = nullptr; p.bp_ws = nullptr;
+  p.out_pose = out_pose; p.out_trace = out_trace;
+
+  // ---- on-chip path: offset-only table, shells within reach, n0 <= 16 ------------------------------
+  OcLayout L;
+  if (use_lut && rpsm_onchip_layout(hm, V, J, H, W, first_nbins, nbR, max_reach, L)) {
+    const int blocks = B < sm ? B : sm;   // one persistent block per SM
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    L.coords_ws = reinterpret_cast<double*>(w);
+    w += align_up((size_t)blocks * V * nb0 * 2 * sizeof(double), 256);
+    L.spill_ws = reinterpret_cast<double*>(w);
+    w += align_up((size_t)blocks * L.nspill * L.vec_stride * sizeof(double), 256);
+    L.bp_ws = reinterpret_cast<uint16_t*>(w);
+    static PerDevice<size_t> attr_set;
+    size_t* have = attr_set.slot();
+    if (have == nullptr) return PB200_ERR_CUDA;
+    if (*have < L.smem_bytes) {
+      PB_CUDA(cudaFuncSetAttribute(rpsm_onchip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOcSmemBudget));
+      *have = (size_t)kOcSmemBudget;
+    }
+    rpsm_onchip_kernel<<<blocks, kOcThreads, L.smem_bytes, (cudaStream_t)stream>>>(p, L);
+    PB_LAUNCH_CHECK("rpsm_onchip_kernel");
+    return PB200_OK;
+  }
+
+  // ---- generic path: arbitrary bit matrices, wide shells, large grids ------------------------------
+  const size_t smem = rpsm_smem_bytes(nb0, J, V, nbR);
+  PB_REQUIRE(smem <= 227 * 1024, "first_nbins=%d needs %zu bytes of shared memory", first_nbins, smem);
+  static PerDevice<size_t> generic_attr;
+  size_t* have = generic_attr.slot();
+  if (have == nullptr) return PB200_ERR_CUDA;
+  if (*have < smem) {
+    PB_CUDA(cudaFuncSetAttribute(rpsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    *have = smem;
+  }
+  const int slots = rpsm_slots(B, sm);
   p.energy_ws = reinterpret_cast<double*>(workspace);
   const size_t e_bytes = (((size_t)slots * J * nb0 * sizeof(double) + 255) / 256) * 256;
   p.bp_ws = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(workspace) + e_bytes);
-  p.out_pose = out_pose; p.out_trace = out_trace;
   rpsm_kernel<<<slots, kRpsmThreads, smem, (cudaStream_t)stream>>>(p);
   PB_LAUNCH_CHECK("rpsm_kernel");
   return PB200_OK;

@@ -41,20 +41,33 @@ class PairwiseTable(object):
         self.bits = bits
         self.nbins = nbins
         self._offset_only = None
+        self._max_reach = -1
+
+    def _check(self):
+        n = int(round(self.nbins ** (1.0 / 3)))
+        if n ** 3 != self.nbins:
+            self._offset_only, self._max_reach = False, -1
+        else:
+            flag = rt.zeros((2,), torch.int32)
+            _lib.call('pb200_pairwise_lut_check', rt.ptr(self.bits), int(self.bits.shape[0]), n,
+                      rt.ptr(flag), rt.stream_ptr())
+            bad, reach = [int(v) for v in flag.cpu()]
+            self._offset_only, self._max_reach = bad == 0, reach
 
     @property
     def offset_only(self):
         """True if P[i,j] depends on the index offset (|dy|,|dx|,|dz|) only (checked once, on the GPU)."""
         if self._offset_only is None:
-            n = int(round(self.nbins ** (1.0 / 3)))
-            if n ** 3 != self.nbins:
-                self._offset_only = False
-            else:
-                flag = rt.zeros((1,), torch.int32)
-                _lib.call('pb200_pairwise_lut_check', rt.ptr(self.bits), int(self.bits.shape[0]), n,
-                          rt.ptr(flag), rt.stream_ptr())
-                self._offset_only = int(flag.item()) == 0
+            self._check()
         return self._offset_only
+
+    @property
+    def max_reach(self):
+        """Largest |bin offset| of an allowed pair in row 0 of any edge (decides, with ``offset_only``,
+        whether level 0 can run on chip; checked once, on the GPU)."""
+        if self._offset_only is None:
+            self._check()
+        return self._max_reach
 
     @classmethod
     def from_dict(cls, pairwise, body):
@@ -97,7 +110,7 @@ class PairwiseTable(object):
 
 
 def rpsm_batch(cams, heatmaps, boxes_center, boxes_scale, grid_centers, limb_lengths, pairwise,
-               config, body=None, return_trace=False, use_lut=True):
+               config, body=None, return_trace=False, use_lut=True, onchip=True):
     """RPSM for B frames.
 
     cams         : CameraTable or list of B*V camera dicts (view-minor rows)
@@ -107,6 +120,8 @@ def rpsm_batch(cams, heatmaps, boxes_center, boxes_scale, grid_centers, limb_len
     limb_lengths : [B, E] float64 in ``body.edges()`` order
     pairwise     : PairwiseTable or the reference's dict
     use_lut      : allow the shared-memory offset table when the pairwise matrix permits it
+    onchip       : allow the on-chip level 0 (csrc/rpsm.cu::rpsm_onchip_kernel) when the table and the
+                   grid permit it; False forces the generic kernel (same results, used by the tests)
     Returns poses [B, J, 3] float64 (CUDA tensor if heatmaps is one), optionally the chosen
     bins per level [B, depth+1, J] int32.
     """
@@ -148,7 +163,7 @@ def rpsm_batch(cams, heatmaps, boxes_center, boxes_scale, grid_centers, limb_len
     _lib.call('pb200_rpsm', rt.ptr(hm), B, V, J, H, W, rt.ptr(table.pack), rt.ptr(table.index),
               rt.ptr(aff), int(img[0]), int(img[1]), rt.ptr(root), rt.ptr(limb),
               rt.ptr(d_edges), rt.ptr(d_order), root_idx, rt.ptr(pw.bits), int(pw.offset_only and use_lut),
-              n0, int(ps.RECUR_NBINS), depth, float(ps.GRID_SIZE), float(ps.LIMB_LENGTH_TOLERANCE),
+              int(pw.max_reach) if (onchip and use_lut and pw.offset_only) else -1, n0, int(ps.RECUR_NBINS), depth, float(ps.GRID_SIZE), float(ps.LIMB_LENGTH_TOLERANCE),
               rt.ptr(ws), int(ws.numel()), rt.ptr(pose), rt.ptr(trace), rt.stream_ptr())
     if not rt.is_device_tensor(heatmaps):
         pose = rt.to_host(pose)

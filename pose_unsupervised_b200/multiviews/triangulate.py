@@ -93,9 +93,19 @@ class LiftResult(object):
 
 
 def _lift_launch(views, B, nviews, J, H, W, affine, post_process, pack, index, no_distortion, conf_thre,
-                 xy, maxvals, idx, poses3d, err, proj, fmat, slots, resid):
-    """One pb200_lift_fused call on device tensors (outputs preallocated by the caller)."""
+                 xy, maxvals, idx, poses3d, err, proj, fmat, slots, resid, after_decode=None):
+    """One pb200_lift_fused call on device tensors (outputs preallocated by the caller); with
+    ``after_decode`` the two launches are issued separately and the callable runs in between."""
     ptrs = (ctypes.c_void_p * len(views))(*[v.data_ptr() for v in views])
+    if after_decode is not None:
+        _lib.call('pb200_decode', ptrs, len(views), B * nviews, J, H, W, rt.ptr(affine), int(bool(post_process)),
+                  rt.ptr(xy), rt.ptr(maxvals), rt.ptr(idx), rt.stream_ptr())
+        after_decode()
+        _lib.call('pb200_lift_decoded', rt.ptr(pack), rt.ptr(index), rt.ptr(xy), rt.ptr(maxvals),
+                  int(conf_thre is not None), float(0.0 if conf_thre is None else conf_thre), B, nviews, J,
+                  int(bool(no_distortion)), rt.ptr(poses3d), rt.ptr(err), rt.ptr(proj), rt.ptr(fmat),
+                  rt.ptr(slots), rt.ptr(resid), rt.stream_ptr())
+        return
     _lib.call('pb200_lift_fused', ptrs, len(views), B, nviews, J, H, W, rt.ptr(affine),
               int(bool(post_process)), rt.ptr(pack), rt.ptr(index),
               int(bool(no_distortion)), int(conf_thre is not None),
@@ -178,7 +188,7 @@ def _lift_from_pageable(hm, B, nviews, J, H, W, affine, post_process, table, no_
 
 def lift_heatmaps(heatmaps, center, scale, camera_params, nviews=4, post_process=True,
                   no_distortion=False, conf_thre=None, return_idx=False, return_proj=False,
-                  affine=None, out_poses3d=None, fundamental=None, subjects=None):
+                  affine=None, out_poses3d=None, fundamental=None, subjects=None, after_decode=None):
     """Heatmaps -> 2D joints -> 3D poses -> reprojection error in one pass over HBM.
 
     Equivalent to ``get_final_preds`` (lib/core/inference.py:50-75) on every row followed by
@@ -191,6 +201,10 @@ def lift_heatmaps(heatmaps, center, scale, camera_params, nviews=4, post_process
     send buffer of ``parallel.PoseExchange``).  With ``fundamental`` (a ``core.loss.FundamentalTable``)
     and ``subjects`` [B], the algebraic epipolar residuals of the decoded coordinates
     (run/test/test_fund_mtx.py:56-69) are produced in the same pass as ``result.epipolar``.
+
+    ``after_decode``: a callable run between the decode launch and the lift launch (device-resident
+    input only); ``parallel.PoseExchange.pipelined_step`` uses it to start the previous step's
+    all-gather underneath the latency-bound lift kernel.
 
     A numpy array in pageable host memory (what ``validate()`` hands over after ``.cpu().numpy()``,
     lib/core/function.py:633-640) is streamed to the device in chunks through two pinned staging
@@ -245,7 +259,7 @@ def lift_heatmaps(heatmaps, center, scale, camera_params, nviews=4, post_process
                             no_distortion, conf_thre, (xy, maxvals, idx, poses3d, err, proj, resid), fmat, slots)
     else:
         _lift_launch(views, B, nviews, J, H, W, affine, post_process, table.pack, table.index, no_distortion,
-                     conf_thre, xy, maxvals, idx, poses3d, err, proj, fmat, slots, resid)
+                     conf_thre, xy, maxvals, idx, poses3d, err, proj, fmat, slots, resid, after_decode)
     return LiftResult(xy, maxvals, idx, poses3d, err, proj, resid)
 
 

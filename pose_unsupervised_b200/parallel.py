@@ -100,23 +100,34 @@ class PoseExchange(object):
             self.recv[slot].copy_(self.send[slot])
 
     def pipelined_step(self, k, compute):
-        """Step ``k`` of a double-buffered loop: ``compute(slot)`` fills slot ``k % nslots`` on the
-        current stream while the all-gather of the previous step's slot runs on the side stream.
-        Fork and join are stream waits, so the step is capturable in a CUDA graph (one graph per
-        slot).  The last step's slot is still to be gathered afterwards: ``run((K-1) % nslots)``.
+        """Step ``k`` of a double-buffered loop: ``compute(slot, fork)`` fills slot ``k % nslots`` on the
+        current stream; the all-gather of the previous step's slot runs on the side stream from the
+        moment ``compute`` calls ``fork()`` (at the latest when it returns).  Forking after the
+        HBM-bound decode and before the small latency-bound kernels puts the collective where SMs are
+        idle.  Fork and join are stream waits, so the step is capturable in a CUDA graph (one graph
+        per slot).  The last step's slot is still to be gathered afterwards: ``run((K-1) % nslots)``.
         """
         cur, prev = k % self.nslots, (k - 1) % self.nslots
         if self.world == 1:
-            return compute(cur)
-        if self.side is None:                       # CPU tensors (gloo tests): same order, no overlap
-            self.run(prev)
-            return compute(cur)
-        main = torch.cuda.current_stream()
-        self.side.wait_stream(main)                 # fork: step k-1 has finished on `main`
-        with torch.cuda.stream(self.side):
-            self.run(prev)
-        out = compute(cur)
-        main.wait_stream(self.side)                 # join
+            return compute(cur, lambda: None)
+        state = {'forked': False}
+        main = torch.cuda.current_stream() if self.side is not None else None
+
+        def fork():
+            if state['forked']:
+                return
+            state['forked'] = True
+            if self.side is None:                   # CPU tensors (gloo tests): same order, no overlap
+                self.run(prev)
+                return
+            self.side.wait_stream(main)             # everything issued so far, step k-1 included, is ahead
+            with torch.cuda.stream(self.side):
+                self.run(prev)
+
+        out = compute(cur, fork)
+        fork()
+        if self.side is not None:
+            main.wait_stream(self.side)             # join
         return out
 
     def gathered_poses(self, slot=0):

@@ -1,0 +1,10 @@
+#!/bin/bash
+# round-2 GPU check of the on-chip RPSM kernel: parity tests, throughput (with / without L2 hints), ncu.
+set -u
+OUT=gpurun_out/r2c; mkdir -p $OUT
+timeout 900 python -m pytest tests/test_gpu_rpsm.py -x -q > $OUT/pytest_rpsm.log 2>&1; echo "pytest_rpsm rc=$?" | tee -a $OUT/pytest_rpsm.log
+timeout 300 python bench.py --workload rpsm --steps 5 > $OUT/rpsm.log 2>&1; echo "rpsm rc=$?"
+timeout 300 python bench.py --workload rpsm --steps 5 --frames 2368 --no-cpu-baseline > $OUT/rpsm_2368.log 2>&1; echo "rpsm2368 rc=$?"
+PB200_LIB=$PWD/pose_unsupervised_b200/libposeb200_nohint.so timeout 300 python bench.py --workload rpsm --steps 5 --frames 2368 --no-cpu-baseline > $OUT/rpsm_2368_nohint.log 2>&1; echo "rpsm nohint rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:rpsm_onchip -c 1 -o $OUT/prof_rpsm_onchip python bench.py --workload rpsm --steps 1 --frames 592 --no-cpu-baseline > $OUT/ncu_rpsm.log 2>&1; echo "ncu rc=$?"
+tail -3 $OUT/rpsm.log $OUT/rpsm_2368.log $OUT/rpsm_2368_nohint.log

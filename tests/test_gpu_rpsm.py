@@ -197,3 +197,91 @@ def test_rpsm_wide_shells_take_the_sorted_walk(pict):
                                      np.array([[limb[e] for e in edges]]), table, cfg, body,
                                      return_trace=True, use_lut=use_lut)
         assert np.array_equal(trace[0], rtrace) and np.array_equal(got[0], ref), use_lut
+
+
+@pytest.mark.parametrize('nviews,hw,nframes', [(4, 64, 330), (8, 64, 24), (4, 96, 24), (2, 80, 24), (3, 63, 12)])
+def test_rpsm_onchip_equals_generic_kernel(pict, nviews, hw, nframes):
+    """The on-chip level 0 (staged heatmaps, shared-memory energies, pruned max, zero shortcut) and the
+    generic kernel are two implementations of the same arithmetic: identical bins at every level and
+    identical poses.  330 frames > 2 x 148 SMs: every persistent block processes several frames, so the
+    cross-frame prefetch is exercised; 8 views / 96^2 / 80^2 maps need several staged groups per joint;
+    63^2 maps are not 16-byte sized and are sampled with plain loads.  Degenerate frames (all-negative and
+    all-zero joints) force the redo-without-shortcut pass in the middle of the batch."""
+    from pose_unsupervised_b200.multiviews.body import HumanBody
+    body, obody = HumanBody.h36m17(), h36m17()
+    edges = obody.edges()
+    cfg = rpsm_config(depth=4)
+    cfg.NETWORK.HEATMAP_SIZE = np.array([hw, hw])
+    base = 6
+    rng = np.random.default_rng(nviews * 1000 + hw)
+    avg = {e: float(np.mean([np.linalg.norm(p[e[0]] - p[e[1]]) for p in synth.random_poses(64, seed=99)]))
+           for e in edges}
+    table = pict.PairwiseTable.from_limb_lengths(avg, body, 2000, 16)
+    assert table.offset_only and 0 < table.max_reach <= 5
+    frames = []
+    for f in range(base):
+        pose = synth.random_poses(1, seed=200 + f)[0]
+        cams = synth.camera_ring(nviews, seed=300 + f)
+        boxes = synth.crop_box(cams, pose)
+        hm = synth.gaussian_heatmaps(cams, boxes, pose, hw, 256, 2.0 * hw / 64, 0.02, seed=f)
+        if f == 3:
+            hm[:, [0, 5, 9]] = -hm[:, [0, 5, 9]] - 0.01
+        if f == 4:
+            hm[:, [10, 15]] = 0.0
+        if f == 5:
+            hm = (hm - 0.05).astype(np.float32)
+        frames.append((pose, cams, boxes, hm, synth.limb_lengths(pose, edges)))
+    pick = rng.integers(0, base, nframes)
+    pick[:base] = np.arange(base)                       # every kind of frame is present
+    hms = np.array([frames[i][3] for i in pick])
+    cams = [c for i in pick for c in frames[i][1]]
+    centers = np.array([b['center'] for i in pick for b in frames[i][2]])
+    scales = np.array([b['scale'] for i in pick for b in frames[i][2]])
+    roots = np.array([frames[i][0][0] for i in pick]) + rng.normal(0, 40.0, (nframes, 3))
+    limbs = np.array([[frames[i][4][e] for e in edges] for i in pick])
+    args = (cams, hms, centers, scales, roots, limbs, table, cfg, body)
+    p_on, t_on = pict.rpsm_batch(*args, return_trace=True, onchip=True)
+    p_gen, t_gen = pict.rpsm_batch(*args, return_trace=True, onchip=False)
+    assert np.array_equal(t_on, t_gen)
+    assert np.array_equal(p_on, p_gen)
+    # and one frame of each kind against the oracle itself
+    for kind in (0, 3, 4):
+        f = int(np.where(pick == kind)[0][0])
+        boxes = [{'center': centers[f * nviews + v], 'scale': scales[f * nviews + v]} for v in range(nviews)]
+        limb = {e: limbs[f][k] for k, e in enumerate(edges)}
+        ref, rtrace = opict.rpsm(cams[f * nviews:(f + 1) * nviews], hms[f], boxes, roots[f], limb,
+                                 opict.level0_pairwise(2000, avg, 16, obody), cfg, obody, return_trace=True)
+        assert np.array_equal(t_on[f], rtrace) and np.array_equal(p_on[f], ref), kind
+
+
+def test_rpsm_onchip_spills_vectors_for_deep_trees(pict):
+    """A caterpillar tree (every spine joint has a leaf as FIRST child) keeps one accumulator alive per
+    spine joint: more live energy vectors than fit in shared memory, so some are spilled to scratch.
+    Same bins as the generic kernel and as the oracle."""
+    from pose_unsupervised_b200.multiviews.body import HumanBody
+    J = 17
+    children = [[] for _ in range(J)]
+    spine = list(range(0, J, 2))                      # 0, 2, 4, ..., 16
+    for a, b in zip(spine[:-1], spine[1:]):
+        children[a] = [a + 1, b]                      # leaf first, then the rest of the spine
+    names = ['j%d' % i for i in range(J)]
+    body = HumanBody(names, children, 0)
+    obody = OracleBody(names, children, 0)
+    edges = obody.edges()
+    cfg = rpsm_config(depth=2)
+    pose = synth.random_poses(1, seed=5)[0]
+    cams = synth.camera_ring(4, seed=6)
+    boxes = synth.crop_box(cams, pose)
+    hm = synth.gaussian_heatmaps(cams, boxes, pose, 64, 256, 2.0, 0.02, seed=7)
+    limb = synth.limb_lengths(pose, edges)
+    avg = {e: min(max(limb[e], 150.0), 420.0) for e in edges}
+    table = pict.PairwiseTable.from_limb_lengths(avg, body, 2000, 16)
+    assert table.offset_only and table.max_reach <= 5
+    args = (cams, hm[None], np.array([b['center'] for b in boxes]), np.array([b['scale'] for b in boxes]),
+            pose[0][None], np.array([[limb[e] for e in edges]]), table, cfg, body)
+    p_on, t_on = pict.rpsm_batch(*args, return_trace=True, onchip=True)
+    p_gen, t_gen = pict.rpsm_batch(*args, return_trace=True, onchip=False)
+    assert np.array_equal(t_on, t_gen) and np.array_equal(p_on, p_gen)
+    ref, rtrace = opict.rpsm(cams, hm, boxes, pose[0], limb, opict.level0_pairwise(2000, avg, 16, obody), cfg,
+                             obody, return_trace=True)
+    assert np.array_equal(t_on[0], rtrace) and np.array_equal(p_on[0], ref)

@@ -44,8 +44,10 @@ def _worker(rank, world, port, nframes, q):
         # double-buffered form: the gather of step k-1 is issued in step k, the last one drained
         ex2 = parallel.PoseExchange(nframes, 17, torch.device('cpu'), nslots=2)
         for k in range(3):
-            def compute(slot, k=k):
+            def compute(slot, fork, k=k):
                 ex2.poses_view(slot).copy_(pred[lo:hi] + k)
+                if k == 1:
+                    fork()                      # mid-step fork, as bench.py does after the decode
                 ex2.stats_view(slot).copy_(stats)
             ex2.pipelined_step(k, compute)
             if k >= 1:
