@@ -368,24 +368,47 @@ PB_HD void grid_to_heatmap(const Cam& c, const double aff[6], const double X[3],
 }
 
 // scipy RegularGridInterpolator(linear, bounds_error=False, fill_value=0) on float32
-// values, term order and weights as scipy's generic path (pictorial.py:176-187).
-template <typename LoadF>
-PB_HD double bilinear_zero_outside(LoadF load, int w, int h, double x, double y) {
-  if (x != x || y != y) return x + y;                       // NaN in -> NaN out
-  if (x < 0.0 || x > (double)(w - 1) || y < 0.0 || y > (double)(h - 1)) return 0.0;
+// values, term order and weights as scipy's generic path (pictorial.py:176-187), in two halves: the
+// part that depends only on the sample position (shared by all joints of a view) and the part that
+// reads the map.
+//   pos >= 0 : y0 * w + x0 of the top-left tap;  kBilinearOutside : the sample is 0;
+//   kBilinearNaN : a NaN coordinate gives NaN (fx then carries x + y)
+constexpr int kBilinearOutside = -1;
+constexpr int kBilinearNaN = -2;
+
+PB_HD void bilinear_prepare(int w, int h, double x, double y, int& pos, double& fx, double& fy) {
+  fx = 0.0; fy = 0.0;
+  if (x != x || y != y) { pos = kBilinearNaN; fx = x + y; return; }
+  if (x < 0.0 || x > (double)(w - 1) || y < 0.0 || y > (double)(h - 1)) { pos = kBilinearOutside; return; }
   int x0 = (int)floor(x), y0 = (int)floor(y);
   if (x0 > w - 2) x0 = w - 2;
   if (y0 > h - 2) y0 = h - 2;
   if (x0 < 0) x0 = 0;
   if (y0 < 0) y0 = 0;
-  const double fx = x - (double)x0, fy = y - (double)y0;
+  fx = x - (double)x0;
+  fy = y - (double)y0;
+  pos = y0 * w + x0;
+}
+
+// load(k): the float32 map value at flat index k
+template <typename LoadF>
+PB_HD double bilinear_apply(LoadF load, int w, int pos, double fx, double fy) {
+  if (pos < 0) return pos == kBilinearNaN ? fx : 0.0;
   const double gx = 1.0 - fx, gy = 1.0 - fy;
   double val = 0.0;
-  val = val + (double)load(y0, x0) * (gx * gy);
-  val = val + (double)load(y0 + 1, x0) * (gx * fy);
-  val = val + (double)load(y0, x0 + 1) * (fx * gy);
-  val = val + (double)load(y0 + 1, x0 + 1) * (fx * fy);
+  val = val + (double)load(pos) * (gx * gy);
+  val = val + (double)load(pos + w) * (gx * fy);
+  val = val + (double)load(pos + 1) * (fx * gy);
+  val = val + (double)load(pos + w + 1) * (fx * fy);
   return val;
+}
+
+template <typename LoadF>
+PB_HD double bilinear_zero_outside(LoadF load, int w, int h, double x, double y) {
+  int pos;
+  double fx, fy;
+  bilinear_prepare(w, h, x, y, pos, fx, fy);
+  return bilinear_apply(load, w, pos, fx, fy);
 }
 
 }  // namespace pb200

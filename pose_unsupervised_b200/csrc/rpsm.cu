@@ -82,7 +82,7 @@ __device__ __forceinline__ double sample_view(const RpsmParams& p, const RpsmSha
   grid_to_heatmap(s.cam[v], s.aff[v], X, p.W, p.H, p.img_w, p.img_h, hx, hy);
   const float* m = p.hm + (((size_t)f * p.V + v) * p.J + j) * (size_t)(p.H * p.W);
   const int W = p.W;
-  return bilinear_zero_outside([m, W](int y, int x) { return __ldg(m + y * W + x); }, p.W, p.H, hx, hy);
+  return bilinear_zero_outside([m](int t) { return __ldg(m + t); }, p.W, p.H, hx, hy);
 }
 
 // unary of joint j at world point X: views accumulated in order from 0.0
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kRpsmThreads, 2) rpsm_kernel(const RpsmParams 
         double u = 0.0;
         for (int v = 0; v < V; ++v) {
           const float* m = p.hm + (((size_t)f * V + v) * J + j) * HW;
-          u = u + bilinear_zero_outside([m, W](int y, int x) { return __ldg(m + y * W + x); }, p.W, p.H,
+          u = u + bilinear_zero_outside([m](int t) { return __ldg(m + t); }, p.W, p.H,
                                         hx[v], hy[v]);
         }
         energy[(size_t)j * nb0 + b] = u;
@@ -518,8 +518,8 @@ __global__ void __launch_bounds__(kRpsmThreads, 2) rpsm_kernel(const RpsmParams 
 // shells within +-kRpsmEnumReach bins and n0 <= 16, i.e. every table built on the regular grid).
 //
 // One persistent 1024-thread block per SM; per frame
-//   * the heatmap coordinates of every (bin, view) are computed once (they do not depend on the
-//     joint) and parked in an L2-resident scratch of V*nb0*16 bytes per block;
+//   * the joint-independent half of every bilinear sample (top-left tap and the two fractions of each
+//     (bin, view)) is computed once and parked in an L2-resident scratch of V*nb0*20 bytes per block;
 //   * the tree is walked depth-first by a small program built once per block (thread 0): every
 //     joint's unary is sampled exactly when it is first needed, from ITS V heatmaps staged in shared
 //     memory by the copy engine (cp.async.bulk + mbarrier; the next joint's maps -- or the next
@@ -554,12 +554,14 @@ struct OcOp {
 
 struct OcLayout {   // filled by the host (rpsm_onchip_layout)
   int stage_off, stage_views;   // staged views per group; 0 = sample with __ldg (odd-sized / huge maps)
-  int dzm_off, dzm_cap;         // uint16 entries: allowed |dz| per (edge, |dy|, |dx|)
+  int dzm_off, dzm_cap;         // uint16 entries: allowed |dz| per (edge, |dy|, dx)
+  int list_off, list_cap;       // 8-byte entries: the edges' sorted child-offset lists
   int refine_off;
-  int vec_off, vec_stride;      // vec_stride doubles per vector: nb0 + n0^2 (rounded up to even)
+  int vec_off, vec_stride;      // vec_stride doubles per vector: nb0 (rounded up to even)
   int nsm, nspill;              // vectors in shared memory / in scratch per block
   size_t smem_bytes;
-  double* coords_ws;            // [blocks][V][nb0][2]
+  double* coords_ws;            // [blocks][V][nb0][2]  bilinear fractions
+  int32_t* tap_ws;              // [blocks][V][nb0]     top-left tap of the sample
   double* spill_ws;             // [blocks][nspill][vec_stride]
   uint16_t* bp_ws;              // [blocks][E][nb0]
 };
@@ -570,7 +572,9 @@ struct OcShared {
   int nops, nsamp, root_buf, prog_err;
   int reach[kRpsmMaxJ];
   int doff[kRpsmMaxJ + 1];      // offset of edge e in the |dz| table
-  int contig[kRpsmMaxJ];        // 1: every |dz| set of the edge is one run (a spherical shell)
+  int loff[kRpsmMaxJ][8];       // offset / (even) length of the offset-list slice of (edge, |oy|)
+  int lcnt[kRpsmMaxJ][8];
+  int use_flat;                 // 1: the offset lists of all edges fit in shared memory and n0 = 16
   int child_start[kRpsmMaxJ + 1];
   uint8_t child_edge[kRpsmMaxJ];
   uint8_t samp_joint[kRpsmMaxJ];
@@ -851,91 +855,79 @@ __device__ __forceinline__ unsigned oc_lds16(uint32_t a) {
   asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
   return v;
 }
-// One candidate child at shared address `a`: it becomes the running first maximum iff k is inside the
-// lane's range and its energy is STRICTLY larger (children are visited in ascending index order).
-__device__ __forceinline__ void oc_cand_ge(uint32_t a, int k, int lo, double& best, uint32_t& fa) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      ".reg .f64 v;\n\t"
-      "ld.shared.f64 v, [%2];\n\t"
-      "setp.ge.s32 q, %3, %4;\n\t"
-      "setp.gt.and.f64 p, v, %0, q;\n\t"
-      "selp.f64 %0, v, %0, p;\n\t"
-      "selp.b32 %1, %2, %1, p;\n\t"
-      "}" : "+d"(best), "+r"(fa) : "r"(a), "r"(k), "r"(lo) : "memory");
+__device__ __forceinline__ uint4 oc_lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
 }
-__device__ __forceinline__ void oc_cand_le(uint32_t a, int k, int hi, double& best, uint32_t& fa) {
+// One candidate child from an edge's offset list.  `o2` = (ox + 8) | (k + 8) << 8, `d8` = (ox*16 + k)*8;
+// p2 = (ix + 8) | (iz + 8) << 8 of the lane's parent (0 for a lane that sits this task out).  Both child
+// coordinates are inside the 16-wide grid iff bits 4-5 of both byte sums read 01.  The child becomes the
+// running first maximum iff it is inside and STRICTLY larger -- children come in ascending index order.
+__device__ __forceinline__ void oc_cand(uint32_t o2, uint32_t d8, uint32_t p2, uint32_t base, double& best,
+                                        uint32_t& fa) {
   asm volatile(
       "{\n\t"
       ".reg .pred p, q;\n\t"
+      ".reg .b32 s, d;\n\t"
       ".reg .f64 v;\n\t"
-      "ld.shared.f64 v, [%2];\n\t"
-      "setp.le.s32 q, %3, %4;\n\t"
+      "add.u32 s, %2, %4;\n\t"
+      "and.b32 s, s, 0x3030;\n\t"
+      "setp.eq.u32 q, s, 0x1010;\n\t"
+      "add.u32 d, %5, %3;\n\t"
+      "@q ld.shared.f64 v, [d];\n\t"                 /* v is undefined when !q; the compare below is masked by q */
       "setp.gt.and.f64 p, v, %0, q;\n\t"
       "selp.f64 %0, v, %0, p;\n\t"
-      "selp.b32 %1, %2, %1, p;\n\t"
-      "}" : "+d"(best), "+r"(fa) : "r"(a), "r"(k), "r"(hi) : "memory");
+      "selp.b32 %1, d, %1, p;\n\t"
+      "}" : "+d"(best), "+r"(fa) : "r"(o2), "r"(d8), "r"(p2), "r"(base) : "memory");
 }
 
-// One warp task of the max-product: the 32 consecutive parent bins [32u, 32u+32) of edge e.
+// One warp task of the max-product: the 32 consecutive parent bins [32u, 32u+32) of edge e (n0 = 16).
 //   D[i] <- D[i] * max_j ( P[i,j] ? S[j] : 0 ),  bp[i] <- first argmax           (pictorial.py:50-56)
-// FAST FORM (source and destination in shared memory, every |dz| set of the edge one run, finite frame):
-// children are visited by OFFSET (oy, ox, k), the same for every lane, in ascending child index, so all
-// lanes run the same loops and differ only in predicates -- the warp never diverges.  A row of children is
-// skipped when no lane can still be improved by it (row maxima RS); lanes that cannot be improved, or whose
-// row lies outside the grid, load from a harmless address inside the block's shared memory and are masked
-// by their k-range.  sS / sD: shared addresses of the vectors; sDz: the edge's |dz| table
-// [(r+1)][2r+1] uint16 (bit k = |dz| = k allowed), indexed by (|oy|, ox + r).
-__device__ __forceinline__ bool oc_maxprod_unit_smem(uint32_t sS, uint32_t sD, uint16_t* __restrict__ bp_e,
-                                                     uint32_t sDz, const uint32_t* __restrict__ row0, int n0,
-                                                     int nb0, int r, int u, bool skip_ok) {
+// FAST FORM (source and destination in shared memory, finite frame): the allowed children of the edge
+// are a LIST of offsets, sorted by ascending child index and cut into slices by |oy|; it is the same for
+// every parent, so all lanes walk it in lock step -- no divergence, no per-row bookkeeping -- and a lane
+// only masks the children that fall outside the grid.  sList: shared address of the block's lists (8-byte
+// entries), loff / lcnt: offset and (even) length of the edge's slices.
+__device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, uint16_t* __restrict__ bp_e,
+                                                     uint32_t sList, const int* __restrict__ loff,
+                                                     const int* __restrict__ lcnt, const uint32_t* __restrict__ row0,
+                                                     int r, int u, bool skip_ok) {
   const int lane = threadIdx.x & 31;
-  const int i = 32 * u + lane;
-  const bool valid = i < nb0;
-  const int iz = i % n0, qi = i / n0, ix = qi % n0, iy = qi / n0;
-  const double acc = valid ? oc_lds64(sD + (uint32_t)i * 8u) : 0.0;
-  const bool skip = valid && skip_ok && acc == 0.0;   // 0 * (finite max) = 0: argmax resolved only if ever needed
-  const bool active = valid && !skip;
-  const uint32_t sRS = sS + (uint32_t)nb0 * 8u;       // max of every row of n0 z-bins of the source
+  const int i = 32 * u + lane;                        // < 4096: every lane is a parent
+  const int iz = i & 15, ix = (i >> 4) & 15, iy = i >> 8;
+  const double acc = oc_lds64(sD + (uint32_t)i * 8u);
+  const bool skip = skip_ok && acc == 0.0;            // 0 * (finite max) = 0: argmax resolved only if ever needed
   double best = -INFINITY;
   uint32_t fa = 0u;                                   // shared address of the running first maximum
-  if (__any_sync(0xffffffffu, active)) {
-    const int w = 2 * r + 1;
-    const int klo = -iz, khi = n0 - 1 - iz;
-    const uint32_t own = sS + (uint32_t)(valid ? i : 0) * 8u;
+  if (__any_sync(0xffffffffu, !skip)) {
+    const uint32_t p2 = skip ? 0u : (uint32_t)((ix + 8) | ((iz + 8) << 8));
+    const int iyu = u >> 3;                           // all 32 parents of a task share iy
     for (int oy = -r; oy <= r; ++oy) {
-      const bool yok = active && (unsigned)(iy + oy) < (unsigned)n0;
-      if (!__any_sync(0xffffffffu, yok)) continue;
-      uint32_t dza = sDz + (uint32_t)(abs(oy) * w) * 2u;
-      int rowq = qi + oy * n0 - r;                    // child row of this lane for ox = -r
-      for (int ox = -r; ox <= r; ++ox, dza += 2u, ++rowq) {
-        const unsigned dm = oc_lds16(dza);            // same for every lane
-        if (dm == 0u) continue;
-        const bool inrow = yok && (unsigned)(ix + ox) < (unsigned)n0;
-        double rsv = -INFINITY;
-        if (inrow) rsv = oc_lds64(sRS + (uint32_t)rowq * 8u);
-        const bool rowok = rsv > best;
-        if (!__any_sync(0xffffffffu, rowok)) continue;
-        const int a = __ffs(dm) - 1, b = 31 - __clz(dm);
-        const int lo = rowok ? klo : 64, hi = rowok ? khi : -64;
-        const uint32_t base = rowok ? sS + (uint32_t)(rowq * n0 + iz) * 8u : own;
-        for (int k = -b; k <= -a; ++k) oc_cand_ge(base + (uint32_t)(k * 8), k, lo, best, fa);   // below the parent's z
-        for (int k = a > 0 ? a : 1; k <= b; ++k) oc_cand_le(base + (uint32_t)(k * 8), k, hi, best, fa);   // above
+      if ((unsigned)(iyu + oy) >= 16u) continue;
+      const int aoy = oy < 0 ? -oy : oy;
+      const uint32_t base = sS + (uint32_t)((i + oy * 256) * 8);
+      uint32_t la = sList + (uint32_t)loff[aoy] * 8u;
+      const int n = lcnt[aoy];
+#pragma unroll 2
+      for (int t = 0; t < n; t += 2, la += 16u) {
+        const uint4 e = oc_lds128(la);                // two entries, the same for every lane
+        oc_cand(e.x, e.y, p2, base, best, fa);
+        oc_cand(e.z, e.w, p2, base, best, fa);
       }
     }
   }
   bool bad = false;
-  if (active) {
+  if (!skip) {
     const int found = fa != 0u ? (int)((fa - sS) >> 3) : -1;
     double val;
     int arg;
-    oc_finish_max(row0, n0, nb0, iy, ix, iz, found, best, val, arg);
+    oc_finish_max(row0, 16, 4096, iy, ix, iz, found, best, val, arg);
     const double out = acc * val;
     bad = !(fabs(out) <= 1.79769313486231570e308);
     oc_sts64(sD + (uint32_t)i * 8u, out);
     bp_e[i] = (uint16_t)arg;
-  } else if (skip) {
+  } else {
     oc_sts64(sD + (uint32_t)i * 8u, 0.0);
     bp_e[i] = (uint16_t)0xffff;
   }
@@ -957,7 +949,6 @@ __device__ __forceinline__ bool oc_maxprod_unit_exact(const double* S, double* D
     bp_e[i] = (uint16_t)0xffff;
     return false;
   }
-  const double* RS = S + nb0;
   const int w = 2 * r + 1;
   int found = -1;
   double best = 0.0;
@@ -965,7 +956,6 @@ __device__ __forceinline__ bool oc_maxprod_unit_exact(const double* S, double* D
   for (int jy = max(iy - r, 0); jy <= jy1; ++jy)
     for (int jx = jx0; jx <= jx1; ++jx) {
       const int row = jy * n0 + jx;
-      if (found >= 0 && !(RS[row] > best)) continue;
       const unsigned dm = dz[abs(iy - jy) * w + (jx - ix) + r];
       const int base = row * n0;
       for (int jz = 0; jz < n0; ++jz)
@@ -1001,13 +991,14 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
   double* eR = gp + (size_t)J * nbR_ * 3;
   double* sv = eR + (size_t)J * nbR_;
   uint8_t* bpR = reinterpret_cast<uint8_t*>(sv + (size_t)V * J * nbR_);
-  double* coords = L.coords_ws + (size_t)blockIdx.x * V * nb0 * 2;
+  double* coords = L.coords_ws + (size_t)blockIdx.x * V * nb0 * 2;   // (fx, fy) of every (view, bin)
+  int32_t* tappos = L.tap_ws + (size_t)blockIdx.x * V * nb0;         // top-left tap, or outside / NaN
   double* spill = L.spill_ws + (size_t)blockIdx.x * L.nspill * L.vec_stride;
   uint16_t* bp = L.bp_ws + (size_t)blockIdx.x * E * nb0;
   const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&os.mbar);
   const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
   const uint32_t vec_s = (uint32_t)__cvta_generic_to_shared(vec_sm);
-  const uint32_t dzm_s = (uint32_t)__cvta_generic_to_shared(dzm);
+  const uint32_t list_s = (uint32_t)__cvta_generic_to_shared(smem_raw + L.list_off);
   const uint64_t pol_keep = l2_policy_evict_last();
   const uint64_t pol_stream = l2_policy_evict_first();
   auto vec = [&](int b) -> double* {
@@ -1017,7 +1008,7 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
   // ---- once per block: tree program, shell reach and |dz| sets of every edge, task order -------------
   if (tid < E) { s.edge_p[tid] = p.edges[2 * tid]; s.edge_c[tid] = p.edges[2 * tid + 1]; }
   if (tid < J) s.order[tid] = p.order[tid];
-  if (tid < kRpsmMaxJ) { os.reach[tid] = 0; os.contig[tid] = 1; }
+  if (tid < kRpsmMaxJ) os.reach[tid] = 0;
   if (tid == 0) {
     os.stage_tag = -1;
     os.stage_seq = 0;
@@ -1049,10 +1040,6 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
       m |= ((__ldg(row0 + (d >> 5)) >> (d & 31)) & 1u) << dz;
     }
     dzm[t] = (uint16_t)m;
-    if (m != 0u) {
-      const uint32_t run = m >> (__ffs(m) - 1);
-      if ((run & (run + 1u)) != 0u) os.contig[e] = 0;   // more than one run of allowed |dz|
-    }
   }
   // warp tasks sorted by how much of their neighbourhood lies inside the grid (interior first): the
   // dynamic hand-out below then finishes all warps together
@@ -1070,6 +1057,46 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
     os.unit_order[rank] = (uint8_t)u;
   }
   __syncthreads();
+  // ---- the edges' child-offset lists (fast form of the max-product, n0 = 16) ------------------------
+  // Row (e, |oy|, ox) contributes its allowed k = -15..15 in ascending order; rows are laid out slice by
+  // slice (e, |oy|), each padded to an even number of entries with one that is outside for every parent.
+  {
+    int32_t* rowoff = reinterpret_cast<int32_t*>(vec_sm);   // scratch: the energy vectors are not in use yet
+    if (tid == 0) {
+      int off = 0;
+      for (int e = 0; e < E; ++e) {
+        const int r = os.reach[e], w = 2 * r + 1;
+        for (int a = 0; a <= r; ++a) {
+          os.loff[e][a] = off;
+          for (int x = 0; x < w; ++x) {
+            const unsigned m = dzm[os.doff[e] + a * w + x];
+            rowoff[os.doff[e] + a * w + x] = off;
+            off += 2 * __popc(m) - (int)(m & 1u);
+          }
+          off += off & 1;
+          os.lcnt[e][a] = off - os.loff[e][a];
+        }
+      }
+      os.use_flat = (n0 == 16 && off <= L.list_cap) ? 1 : 0;
+    }
+    __syncthreads();
+    if (os.use_flat) {
+      uint2* list = reinterpret_cast<uint2*>(smem_raw + L.list_off);
+      for (int t = tid; t < os.doff[E]; t += T) {
+        int e = 0;
+        while (t >= os.doff[e + 1]) ++e;
+        const int r = os.reach[e], w = 2 * r + 1, local = t - os.doff[e];
+        const int ox = local % w - r, a = local / w;
+        const unsigned m = dzm[t];
+        int o = rowoff[t];
+        for (int k = -15; k <= 15; ++k)
+          if ((m >> (k < 0 ? -k : k)) & 1u)
+            list[o++] = make_uint2((uint32_t)((ox + 8) | ((k + 8) << 8)), (uint32_t)((ox * 16 + k) * 8));
+        if (local % w == w - 1 && ((o - os.loff[e][a]) & 1)) list[o] = make_uint2(0x3030u, 0u);   // padding
+      }
+    }
+    __syncthreads();
+  }
 
   const int ngroups = L.stage_views > 0 ? (V + L.stage_views - 1) / L.stage_views : 0;
   // thread 0: hand group g of sampling slot si of frame fr to the copy engine
@@ -1111,9 +1138,12 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
       double X[3];
       bin_to_point(p.grid_size, n0, b, centre, X);
       for (int v = 0; v < V; ++v) {
-        double hx, hy;
+        double hx, hy, fx, fy;
+        int pos;
         grid_to_heatmap(s.cam[v], s.aff[v], X, p.W, p.H, p.img_w, p.img_h, hx, hy);
-        st_f64x2_hint(coords + ((size_t)v * nb0 + b) * 2, hx, hy, pol_keep);
+        bilinear_prepare(p.W, p.H, hx, hy, pos, fx, fy);   // the joint-independent half of the sample
+        st_f64x2_hint(coords + ((size_t)v * nb0 + b) * 2, fx, fy, pol_keep);
+        tappos[(size_t)v * nb0 + b] = pos;
       }
     }
     // (every thread reads back only the coordinates it wrote itself: no barrier needed)
@@ -1136,10 +1166,11 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
                 const int b = tid + k * T;
                 if (b < nb0)
                   for (int v = v0; v < v1; ++v) {
-                    double hx, hy;
-                    ld_f64x2_hint(coords + ((size_t)v * nb0 + b) * 2, hx, hy, pol_keep);
+                    double fx, fy;
+                    ld_f64x2_hint(coords + ((size_t)v * nb0 + b) * 2, fx, fy, pol_keep);
+                    const int pos = tappos[(size_t)v * nb0 + b];
                     const float* m = stage + (size_t)(v - v0) * HWm;
-                    u[k] = u[k] + bilinear_zero_outside([m, W](int y, int x) { return m[y * W + x]; }, p.W, p.H, hx, hy);
+                    u[k] = u[k] + bilinear_apply([m](int t) { return m[t]; }, W, pos, fx, fy);
                   }
               }
               __syncthreads();   // every thread is done with the stage
@@ -1156,10 +1187,11 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
               const int b = tid + k * T;
               if (b < nb0)
                 for (int v = 0; v < V; ++v) {
-                  double hx, hy;
-                  ld_f64x2_hint(coords + ((size_t)v * nb0 + b) * 2, hx, hy, pol_keep);
+                  double fx, fy;
+                  ld_f64x2_hint(coords + ((size_t)v * nb0 + b) * 2, fx, fy, pol_keep);
+                  const int pos = tappos[(size_t)v * nb0 + b];
                   const float* m = p.hm + (((size_t)f * V + v) * J + op.joint) * (size_t)HWm;
-                  u[k] = u[k] + bilinear_zero_outside([m, W](int y, int x) { return __ldg(m + y * W + x); }, p.W, p.H, hx, hy);
+                  u[k] = u[k] + bilinear_apply([m](int t) { return __ldg(m + t); }, W, pos, fx, fy);
                 }
             }
           }
@@ -1174,19 +1206,11 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
         }
         if (op.kind != kOpLeaf) {
           double* S = vec(op.src);
-          for (int r = tid; r < n0 * n0; r += T) {   // max of every row of n0 z-bins of the source
-            double m = -INFINITY;
-            for (int z = 0; z < n0; ++z) {
-              const double v = S[r * n0 + z];
-              if (v > m) m = v;
-            }
-            S[nb0 + r] = m;
-          }
           if (tid == 0) os.unit_next = 0;
           __syncthreads();
           const int e = op.edge;
           const bool finite = os.nonfinite == 0;
-          const bool uniform = finite && os.contig[e] != 0;
+          const bool flat = finite && os.use_flat != 0 && op.src < L.nsm && op.dst < L.nsm;
           const bool skip_ok = pass == 0 && os.skip_ok != 0 && finite;
           const uint32_t* row0 = p.pair_bits + (size_t)e * nb0 * words0;
           bool bad = false;
@@ -1196,10 +1220,10 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
             t = __shfl_sync(0xffffffffu, t, 0);
             if (t >= nunits) break;
             const int u = os.unit_order[t];
-            if (uniform && op.src < L.nsm && op.dst < L.nsm)   // the fast form: everything on chip
-              bad |= oc_maxprod_unit_smem(vec_s + (uint32_t)((size_t)op.src * L.vec_stride * 8),
+            if (flat)   // everything on chip, every lane walks the edge's offset list
+              bad |= oc_maxprod_unit_flat(vec_s + (uint32_t)((size_t)op.src * L.vec_stride * 8),
                                           vec_s + (uint32_t)((size_t)op.dst * L.vec_stride * 8), bp + (size_t)e * nb0,
-                                          dzm_s + (uint32_t)os.doff[e] * 2u, row0, n0, nb0, os.reach[e], u, skip_ok);
+                                          list_s, os.loff[e], os.lcnt[e], row0, os.reach[e], u, skip_ok);
             else
               bad |= oc_maxprod_unit_exact(S, D, bp + (size_t)e * nb0, dzm + os.doff[e], row0, n0, nb0, os.reach[e],
                                            u, skip_ok);
@@ -1353,8 +1377,9 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static int onchip_max_vectors(int J) { return (J - 1) / 2 + 2; }
 
 static size_t onchip_workspace_bytes(int blocks, int V, int J, int nb0, int n0, int nspill) {
-  const size_t vec_stride = align_up((size_t)nb0 + (size_t)n0 * n0, 2);
+  const size_t vec_stride = align_up((size_t)nb0, 2);
   size_t b = align_up((size_t)blocks * V * nb0 * 2 * sizeof(double), 256);
+  b += align_up((size_t)blocks * V * nb0 * sizeof(int32_t), 256);
   b += align_up((size_t)blocks * nspill * vec_stride * sizeof(double), 256);
   b += align_up((size_t)blocks * (J - 1) * nb0 * sizeof(uint16_t), 256);
   return b;
@@ -1380,15 +1405,21 @@ static bool rpsm_onchip_layout(const float* hm, int V, int J, int H, int W, int 
   L.refine_off = (int)off;
   off = align_up(off + (size_t)J * nbR * (3 + 1 + V) * sizeof(double) + (size_t)E * nbR, 16);
   L.vec_off = (int)off;
-  L.vec_stride = (int)align_up((size_t)nb0 + (size_t)n0 * n0, 2);
+  L.vec_stride = (int)align_up((size_t)nb0, 2);
   const size_t vec_bytes = (size_t)L.vec_stride * sizeof(double);
   if (off + 2 * vec_bytes > (size_t)kOcSmemBudget) return false;   // source + destination must be on chip
   const int need = onchip_max_vectors(J);
-  int nsm = (int)(((size_t)kOcSmemBudget - off) / vec_bytes);
+  const int fit = (int)(((size_t)kOcSmemBudget - off) / vec_bytes);
+  // leave ~16 KiB for the child-offset lists unless that would push one of the 4 vectors the reference
+  // skeletons need off the chip
+  int nsm = (int)(((size_t)kOcSmemBudget - off - 16 * 1024) / vec_bytes);
+  if (nsm < 4) nsm = fit < 4 ? fit : 4;
   if (nsm > need) nsm = need;
   L.nsm = nsm;
   L.nspill = need - nsm;
-  L.smem_bytes = off + (size_t)nsm * vec_bytes;
+  L.list_off = (int)(off + (size_t)nsm * vec_bytes);
+  L.list_cap = (int)(((size_t)kOcSmemBudget - (size_t)L.list_off) / 8);
+  L.smem_bytes = (size_t)L.list_off + (size_t)L.list_cap * 8;
   return true;
 }
 
@@ -1453,6 +1484,8 @@ extern "C" int pb200_rpsm(const float* hm, int B, int V, int J, int H, int W, co
     unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
     L.coords_ws = reinterpret_cast<double*>(w);
     w += align_up((size_t)blocks * V * nb0 * 2 * sizeof(double), 256);
+    L.tap_ws = reinterpret_cast<int32_t*>(w);
+    w += align_up((size_t)blocks * V * nb0 * sizeof(int32_t), 256);
     L.spill_ws = reinterpret_cast<double*>(w);
     w += align_up((size_t)blocks * L.nspill * L.vec_stride * sizeof(double), 256);
     L.bp_ws = reinterpret_cast<uint16_t*>(w);

@@ -67,7 +67,7 @@ void hc_unary(const float* hm, int w, int h, const double* campack, const double
   for (int i = 0; i < n; ++i) {
     double hx, hy;
     grid_to_heatmap(c, aff, pts + 3 * i, w, h, img_w, img_h, hx, hy);
-    out[i] = bilinear_zero_outside([&](int y, int x) { return hm[y * w + x]; }, w, h, hx, hy);
+    out[i] = bilinear_zero_outside([&](int t) { return hm[t]; }, w, h, hx, hy);
   }
 }
 
