@@ -611,7 +611,7 @@ def rpsm_leg(B=592, steps=5, cpu_frames=2):
     err = float(np.mean(np.linalg.norm(got[:prob['base']] - h['poses'], axis=2)))
     res = {'workload': 'configs[2]: RPSM 4 views x 17 joints, 16^3 then 10 x 2^3', 'frames': B,
            'ms_per_step': ms, 'frames_per_s': B / (ms * 1e-3), 'mpjpe_mm_vs_synthetic_gt': err,
-           'gpu_launches': steps, 'kernel': 'rpsm_kernel'}
+           'gpu_launches': steps, 'kernel': 'rpsm_onchip_kernel'}
     if cpu_frames > 0:
         from oracle import pictorial as opict
         from oracle.body import h36m17

@@ -104,6 +104,21 @@ def ransac(poses2d, camera_params, joints_vis, reproj_thre, num_inliers,
     return res_vis
 
 
+def ransac_pairs(poses2d, camera_params, joints_vis, frame, joint, no_distortion=False, nviews=4):
+    """Diagnostics for one (frame, joint) of ``ransac``: for every pair of visible views, in
+    itertools.combinations order, (pair, reprojection error in each of the nviews views).  Tests use it
+    to show that a selection that differs from the GPU's sits on a rounding-level near-tie."""
+    rig = _frame_rig(camera_params, frame, nviews, no_distortion)
+    obs = _visible_obs(poses2d, joints_vis, frame, joint, nviews)
+    out = []
+    for pair in itertools.combinations(obs, 2):
+        X = rig.find3d(list(pair))
+        errs = [float(np.linalg.norm(rig.find2d(_cam_name(j), X) - poses2d[frame * nviews + j, joint, :]))
+                for j in range(nviews)]
+        out.append(((pair[0][0], pair[1][0]), errs))
+    return out
+
+
 def reproject_poses(poses2d, camera_params, joints_vis, no_distortion=False, nviews=4,
                     return_points=False):
     """lib/multiviews/triangulate.py:169-213 -> (proj_2d like poses2d, res_vis like joints_vis)."""

@@ -28,6 +28,13 @@ class FundamentalTable(object):
         for (s, a, b), F in fdict.items():
             if a < nviews and b < nviews:
                 host[self.slot[s], a, b] = np.asarray(F, dtype=np.float64).reshape(9)
+        # the reference indexes the dict per (subject, a, b) and raises KeyError on a missing pair
+        # (lib/core/loss.py:123); a silent zero matrix would make residual and gradient too small
+        missing = [(s, a, b) for s in subjects for a in range(nviews) for b in range(nviews)
+                   if a != b and (s, a, b) not in fdict]
+        if missing:
+            raise KeyError('fundamental matrices missing for (subject, view a, view b): %s%s'
+                           % (missing[:4], ' ...' if len(missing) > 4 else ''))
         self.fmat = rt.to_device(host)
 
     @classmethod
@@ -87,6 +94,10 @@ def epipolar_residuals(pred2d, subjects, fundamental, nviews=4, weight=None, ret
     table = fundamental if isinstance(fundamental, FundamentalTable) else FundamentalTable(fundamental, nviews)
     xy = rt.to_device_float(pred2d)
     N, J = int(xy.shape[0]), int(xy.shape[1])
+    if N % nviews != 0:
+        raise ValueError('%d rows are not a multiple of nviews=%d' % (N, nviews))
+    if table.nviews != nviews:
+        raise ValueError('the fundamental table holds %d views, nviews=%d' % (table.nviews, nviews))
     B = N // nviews
     subj = table.slots(subjects)
     assert int(subj.shape[0]) == B, 'one subject per frame'

@@ -105,21 +105,39 @@ struct PairResult {
 template <typename T>
 __global__ void __launch_bounds__(128) ransac_compact_kernel(GeoParams p, int max_pairs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int cap = 32 * max_pairs;
-  PairResult* res = reinterpret_cast<PairResult*>(smem_raw) + (size_t)warp * cap;
-  PairItem* items = reinterpret_cast<PairItem*>(smem_raw + (size_t)(blockDim.x >> 5) * cap * sizeof(PairResult)) +
-                    (size_t)warp * cap;
   const int V = p.V, J = p.J;
+  // per warp: results and items of its (joint, pair) work list, and the two DLT rows of every
+  // (joint, view) -- undistortion and M = K[R|-RT] are evaluated once per observation, not once per pair
+  PairResult* res = reinterpret_cast<PairResult*>(smem_raw) + (size_t)warp * cap;
+  PairItem* items = reinterpret_cast<PairItem*>(smem_raw + (size_t)nwarps * cap * sizeof(PairResult)) + (size_t)warp * cap;
+  double* rows = reinterpret_cast<double*>(smem_raw + (size_t)nwarps * cap * (sizeof(PairResult) + sizeof(PairItem))) +
+                 (size_t)warp * 32 * V * 8;
   const long long total = (long long)p.B * J;
   const long long g0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane;  // first joint of this warp
   const long long g = g0 + lane;
   const bool valid = g < total;
+  const bool nd = p.no_dist != 0;
   uint32_t mask = 0u;
   if (valid) {
     const int f = (int)(g / J), j = (int)(g % J);
-    for (int v = 0; v < V; ++v)
-      if (p.vis == nullptr || p.vis[((size_t)f * V + v) * J + j]) mask |= 1u << v;
+    const size_t row0 = (size_t)f * V;
+    XYLoader<T> xy{reinterpret_cast<const T*>(p.xy) + (row0 * J + j) * 2, J * 2};
+    for (int v = 0; v < V; ++v) {
+      if (!(p.vis == nullptr || p.vis[(row0 + v) * J + j])) continue;
+      mask |= 1u << v;
+      Cam c;
+      load_cam(p.campack + (size_t)p.cam_index[row0 + v] * PB200_CAM_STRIDE, c);
+      double M[12], u, w, ox, oy, r8[8];
+      proj_matrix(c, M);
+      xy(v, ox, oy);
+      undistort_px(c, nd, ox, oy, u, w);
+      dlt_rows(M, u, w, r8);
+      double* dst = rows + ((size_t)lane * V + v) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dst[k] = r8[k];
+    }
   }
   const int nvis = __popc(mask);
   const int npairs = nvis * (nvis - 1) / 2;
@@ -143,7 +161,6 @@ __global__ void __launch_bounds__(128) ransac_compact_kernel(GeoParams p, int ma
     }
   }
   __syncwarp();
-  const bool nd = p.no_dist != 0;
   for (int it = lane; it < n_items; it += 32) {
     const PairItem q = items[it];
     const long long go = g0 + q.owner;
@@ -151,8 +168,13 @@ __global__ void __launch_bounds__(128) ransac_compact_kernel(GeoParams p, int ma
     const size_t row0 = (size_t)f * V;
     const int32_t* cam_row = p.cam_index + row0;
     XYLoader<T> xy{reinterpret_cast<const T*>(p.xy) + (row0 * J + j) * 2, J * 2};
+    // same accumulation chain as triangulate_joint on views {a, b}: identical bits
+    Sym4 gm;
+    sym4_zero(gm);
+    dlt_add_rows(gm, rows + ((size_t)q.owner * V + q.a) * 8);
+    dlt_add_rows(gm, rows + ((size_t)q.owner * V + q.b) * 8);
     double X[3];
-    triangulate_joint(p.campack, cam_row, V, nd, (1u << q.a) | (1u << q.b), xy, X);
+    dlt_solve(gm, X);
     uint32_t in_mask = 0u;
     int count = 0;
     double err_sum = 0.0;
@@ -359,15 +381,24 @@ extern "C" int pb200_ransac(const double* campack, const int32_t* cam_index, con
   const long long n = (long long)B * J;
   if (n == 0) return PB200_OK;
   const int max_pairs = V * (V - 1) / 2;
-  const size_t smem = (size_t)4 * 32 * max_pairs * (sizeof(pb200::PairResult) + sizeof(pb200::PairItem));
+  const size_t smem = (size_t)4 * 32 * max_pairs * (sizeof(pb200::PairResult) + sizeof(pb200::PairItem)) +
+                      (size_t)4 * 32 * V * 8 * sizeof(double);
   const unsigned blocks = (unsigned)((n + 127) / 128);
-  if (xy_dtype == PB200_F32) {
-    PB_CUDA(cudaFuncSetAttribute(pb200::ransac_compact_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pb200::ransac_compact_kernel<float><<<blocks, 128, smem, (cudaStream_t)stream>>>(p, max_pairs);
-  } else {
-    PB_CUDA(cudaFuncSetAttribute(pb200::ransac_compact_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pb200::ransac_compact_kernel<double><<<blocks, 128, smem, (cudaStream_t)stream>>>(p, max_pairs);
+  // opt in to the shared-memory size once per device and kernel (V = 8 needs 110 KiB), not on every call
+  static PerDevice<size_t> attr_f32, attr_f64;
+  size_t* have = (xy_dtype == PB200_F32 ? attr_f32 : attr_f64).slot();
+  if (have == nullptr) return PB200_ERR_CUDA;
+  if (*have < smem) {
+    if (xy_dtype == PB200_F32)
+      PB_CUDA(cudaFuncSetAttribute(pb200::ransac_compact_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      PB_CUDA(cudaFuncSetAttribute(pb200::ransac_compact_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    *have = smem;
   }
+  if (xy_dtype == PB200_F32)
+    pb200::ransac_compact_kernel<float><<<blocks, 128, smem, (cudaStream_t)stream>>>(p, max_pairs);
+  else
+    pb200::ransac_compact_kernel<double><<<blocks, 128, smem, (cudaStream_t)stream>>>(p, max_pairs);
   PB_LAUNCH_CHECK("ransac_compact_kernel");
   return PB200_OK;
 }

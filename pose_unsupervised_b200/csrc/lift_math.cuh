@@ -150,14 +150,23 @@ PB_HD void sym4_add_row(Sym4& g, const double r[4]) {
   g.a23 = fma(r[2], r[3], g.a23); g.a33 = fma(r[3], r[3], g.a33);
 }
 
+// the two DLT rows of one observation: rows[0..3] = x*M[2]-M[0], rows[4..7] = y*M[2]-M[1]
+PB_HD void dlt_rows(const double M[12], double x, double y, double rows[8]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) rows[j] = x * M[8 + j] - M[j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) rows[4 + j] = y * M[8 + j] - M[4 + j];
+}
+
+PB_HD void dlt_add_rows(Sym4& g, const double rows[8]) {
+  sym4_add_row(g, rows);
+  sym4_add_row(g, rows + 4);
+}
+
 PB_HD void dlt_add_view(Sym4& g, const double M[12], double x, double y) {
-  double r[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) r[j] = x * M[8 + j] - M[j];
-  sym4_add_row(g, r);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) r[j] = y * M[8 + j] - M[4 + j];
-  sym4_add_row(g, r);
+  double rows[8];
+  dlt_rows(M, x, y, rows);
+  dlt_add_rows(g, rows);
 }
 
 // One Jacobi rotation in the (P,Q) plane of the symmetric 4x4 `a` with eigenvector
@@ -167,17 +176,19 @@ template <int P, int Q>
 PB_HD bool jacobi_rotate(double (&a)[4][4], double (&v)[4][4]) {
   const double apq = a[P][Q];
   const double app = a[P][P], aqq = a[Q][Q];
-  // relative criterion (keeps the small eigenpairs of the graded Gram matrix accurate)
-  if (!(fabs(apq) > 1.0e-17 * sqrt(fabs(app) * fabs(aqq))) || apq == 0.0) return false;
-  const double theta = (aqq - app) / (2.0 * apq);
-  double t;
-  if (fabs(theta) > 1.0e150) {
-    t = 0.5 / theta;
-  } else {
-    t = 1.0 / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-    if (theta < 0.0) t = -t;
-  }
+  // relative criterion (keeps the small eigenpairs of the graded Gram matrix accurate):
+  // |apq| > 1e-17 sqrt(|app aqq|), compared in squares to spare the square root
+  if (!(apq * apq > 1.0e-34 * fabs(app * aqq))) return false;
+  // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) with theta = (aqq - app) / (2 apq), written with ONE
+  // division and one square root:  t = sgn(d h) |h| / (|d| + sqrt(d^2 + h^2)),  d = aqq - app, h = 2 apq
+  const double d = aqq - app, h = 2.0 * apq;
+  double t = fabs(h) / (fabs(d) + sqrt(fma(d, d, h * h)));
+  if ((d < 0.0) != (h < 0.0)) t = -t;
+#if defined(__CUDA_ARCH__)
+  const double c = rsqrt(fma(t, t, 1.0));
+#else
   const double c = 1.0 / sqrt(fma(t, t, 1.0));
+#endif
   const double s = t * c;
   a[P][P] = app - t * apq;
   a[Q][Q] = aqq + t * apq;

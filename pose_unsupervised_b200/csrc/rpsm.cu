@@ -538,7 +538,8 @@ __global__ void __launch_bounds__(kRpsmThreads, 2) rpsm_kernel(const RpsmParams 
 // Bit-identical to rpsm_kernel (tests/test_gpu_rpsm.py compares both against the reference golden).
 // =================================================================================================
 #ifndef PB_RPSM_L2_HINTS
-#define PB_RPSM_L2_HINTS 1   // evict_first on the heatmap stream, evict_last on the parked coordinates
+#define PB_RPSM_L2_HINTS 1   // evict_first on the heatmap stream, evict_last on the parked sample taps: same speed,
+                             // DRAM bytes 1.23x instead of 1.50x the algorithmic heatmap bytes (profiles/r02_rpsm_*)
 #endif
 constexpr int kOcThreads = 1024;
 constexpr int kOcMaxPer = 4;                 // level-0 bins per thread: nb0 <= 4096
@@ -592,25 +593,25 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+// parked per-frame data: written once, re-read by every joint -- ask L2 to keep it
+__device__ __forceinline__ void st_keep_f64x2(double* ptr, double a, double b, uint64_t pol) {
+#if PB_RPSM_L2_HINTS
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(ptr), "d"(a), "d"(b), "l"(pol) : "memory");
+#else
+  __stcg(reinterpret_cast<double2*>(ptr), make_double2(a, b));
+#endif
+}
+__device__ __forceinline__ void st_keep_s32(int32_t* ptr, int32_t v, uint64_t pol) {
+#if PB_RPSM_L2_HINTS
+  asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(ptr), "r"(v), "l"(pol) : "memory");
+#else
+  __stcg(ptr, v);
+#endif
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
-}
-__device__ __forceinline__ void st_f64x2_hint(double* ptr, double a, double b, uint64_t pol) {
-#if PB_RPSM_L2_HINTS
-  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(ptr), "d"(a), "d"(b), "l"(pol) : "memory");
-#else
-  reinterpret_cast<double2*>(ptr)[0] = make_double2(a, b);
-#endif
-}
-__device__ __forceinline__ void ld_f64x2_hint(const double* ptr, double& a, double& b, uint64_t pol) {
-#if PB_RPSM_L2_HINTS
-  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(a), "=d"(b) : "l"(ptr), "l"(pol) : "memory");
-#else
-  const double2 v = reinterpret_cast<const double2*>(ptr)[0];
-  a = v.x; b = v.y;
-#endif
 }
 __device__ __forceinline__ void oc_mbar_init(uint32_t bar) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -868,12 +869,13 @@ __device__ __forceinline__ void oc_cand(uint32_t o2, uint32_t d8, uint32_t p2, u
                                         uint32_t& fa) {
   asm volatile(
       "{\n\t"
-      ".reg .pred p, q;\n\t"
+      ".reg .pred p, q, f;\n\t"
       ".reg .b32 s, d;\n\t"
       ".reg .f64 v;\n\t"
       "add.u32 s, %2, %4;\n\t"
-      "and.b32 s, s, 0x3030;\n\t"
-      "setp.eq.u32 q, s, 0x1010;\n\t"
+      "setp.ne.u32 f, 0, 0;\n\t"
+      "lop3.or.b32 s|q, s, 0x3030, 0x1010, 0x6A, f;\n\t"   /* q = ((s & 0x3030) ^ 0x1010) != 0: OUTSIDE */
+      "not.pred q, q;\n\t"
       "add.u32 d, %5, %3;\n\t"
       "@q ld.shared.f64 v, [d];\n\t"                 /* v is undefined when !q; the compare below is masked by q */
       "setp.gt.and.f64 p, v, %0, q;\n\t"
@@ -999,8 +1001,8 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
   const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
   const uint32_t vec_s = (uint32_t)__cvta_generic_to_shared(vec_sm);
   const uint32_t list_s = (uint32_t)__cvta_generic_to_shared(smem_raw + L.list_off);
-  const uint64_t pol_keep = l2_policy_evict_last();
   const uint64_t pol_stream = l2_policy_evict_first();
+  const uint64_t pol_keep = l2_policy_evict_last();
   auto vec = [&](int b) -> double* {
     return b < L.nsm ? vec_sm + (size_t)b * L.vec_stride : spill + (size_t)(b - L.nsm) * L.vec_stride;
   };
@@ -1142,8 +1144,8 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
         int pos;
         grid_to_heatmap(s.cam[v], s.aff[v], X, p.W, p.H, p.img_w, p.img_h, hx, hy);
         bilinear_prepare(p.W, p.H, hx, hy, pos, fx, fy);   // the joint-independent half of the sample
-        st_f64x2_hint(coords + ((size_t)v * nb0 + b) * 2, fx, fy, pol_keep);
-        tappos[(size_t)v * nb0 + b] = pos;
+        st_keep_f64x2(coords + ((size_t)v * nb0 + b) * 2, fx, fy, pol_keep);
+        st_keep_s32(tappos + (size_t)v * nb0 + b, pos, pol_keep);
       }
     }
     // (every thread reads back only the coordinates it wrote itself: no barrier needed)
@@ -1166,11 +1168,10 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
                 const int b = tid + k * T;
                 if (b < nb0)
                   for (int v = v0; v < v1; ++v) {
-                    double fx, fy;
-                    ld_f64x2_hint(coords + ((size_t)v * nb0 + b) * 2, fx, fy, pol_keep);
-                    const int pos = tappos[(size_t)v * nb0 + b];
+                    const double2 fr = __ldcg(reinterpret_cast<const double2*>(coords + ((size_t)v * nb0 + b) * 2));
+                    const int pos = __ldcg(tappos + (size_t)v * nb0 + b);
                     const float* m = stage + (size_t)(v - v0) * HWm;
-                    u[k] = u[k] + bilinear_apply([m](int t) { return m[t]; }, W, pos, fx, fy);
+                    u[k] = u[k] + bilinear_apply([m](int t) { return m[t]; }, W, pos, fr.x, fr.y);
                   }
               }
               __syncthreads();   // every thread is done with the stage
@@ -1187,11 +1188,10 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
               const int b = tid + k * T;
               if (b < nb0)
                 for (int v = 0; v < V; ++v) {
-                  double fx, fy;
-                  ld_f64x2_hint(coords + ((size_t)v * nb0 + b) * 2, fx, fy, pol_keep);
-                  const int pos = tappos[(size_t)v * nb0 + b];
+                  const double2 fr = __ldcg(reinterpret_cast<const double2*>(coords + ((size_t)v * nb0 + b) * 2));
+                  const int pos = __ldcg(tappos + (size_t)v * nb0 + b);
                   const float* m = p.hm + (((size_t)f * V + v) * J + op.joint) * (size_t)HWm;
-                  u[k] = u[k] + bilinear_apply([m](int t) { return __ldg(m + t); }, W, pos, fx, fy);
+                  u[k] = u[k] + bilinear_apply([m](int t) { return __ldg(m + t); }, W, pos, fr.x, fr.y);
                 }
             }
           }

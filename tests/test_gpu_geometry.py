@@ -92,9 +92,45 @@ def test_ransac_vs_oracle(tri, nviews, num_inliers):
         ref = otri.ransac(obs, cams, vis, 10.0, num_inliers, nd, nviews=nviews)
         out = tri.ransac(obs, cams, vis, pseudo_config(10.0, num_inliers, nd), nviews=nviews)
         assert out.dtype == vis.dtype
-        # selection is discrete: a reprojection error within 1e-6 px of the threshold may flip
-        assert (out != ref).mean() < 1e-3
         assert 0.2 < ref.mean() < 1.0
+        # selection is discrete; a (frame, joint) may only differ from the oracle if it sits on a
+        # rounding-level near-tie: some pair has a reprojection error within 1e-6 px of the threshold, or
+        # two pairs with the same number of inliers have mean inlier errors within 1e-9 px of each other
+        diff = (out != ref).reshape(-1, nviews, obs.shape[1]).any(axis=1)
+        assert diff.mean() < 1e-3
+        for f, j in zip(*np.where(diff)):
+            pairs = otri.ransac_pairs(obs, cams, vis, int(f), int(j), nd, nviews=nviews)
+            near_thre = any(abs(e - 10.0) < 1e-6 for _, errs in pairs for e in errs)
+            stats = [(sum(e < 10.0 for e in errs), np.mean([e for e in errs if e < 10.0] or [0.0]))
+                     for _, errs in pairs]
+            near_tie = any(a[0] == b[0] and abs(a[1] - b[1]) < 1e-9
+                           for k, a in enumerate(stats) for b in stats[k + 1:])
+            assert near_thre or near_tie, (f, j, pairs)
+
+
+def test_ransac_pairs_use_the_triangulation_arithmetic_bit_for_bit(tri):
+    """RANSAC keeps the two DLT rows of every observation in shared memory and re-assembles the Gram
+    matrix per pair; the point it scores must be the one `triangulate_poses` computes for the same two
+    views (same accumulation chain, same Jacobi).  With exactly two visible views per joint RANSAC's answer
+    is a function of that point alone, so it can be recomputed from the public entry points."""
+    nviews = 4
+    poses, obs, cams = _scene(nviews, 64, 2.0, outliers=0.2, seed=21)
+    rng = np.random.default_rng(22)
+    B, J = 64, obs.shape[1]
+    vis = np.zeros((B, nviews, J))
+    for f in range(B):
+        for j in range(J):
+            a, b = rng.choice(nviews, 2, replace=False)
+            vis[f, a, j] = vis[f, b, j] = 1
+    vis = vis.reshape(B * nviews, J)
+    for num_inliers in (2, 3):
+        out = tri.ransac(obs, cams, vis, pseudo_config(10.0, num_inliers, False), nviews=nviews)
+        proj, pvis, pts = tri.reproject_poses(obs, cams, vis, False, nviews=nviews, return_points=True)
+        err = np.sqrt(((proj - obs) ** 2)[..., 0] + ((proj - obs) ** 2)[..., 1])       # float64, unfused like the kernel
+        inl = (err < 10.0).reshape(B, nviews, J)
+        keep = inl.sum(axis=1, keepdims=True) >= num_inliers
+        expect = (inl & keep).reshape(B * nviews, J).astype(vis.dtype)
+        assert np.array_equal(out, expect), num_inliers
 
 
 def test_epipolar_vs_oracle():
@@ -278,3 +314,18 @@ def test_differentiable_epipolar_term_vs_torch_autograd():
     for o, r in zip(a_in, b_in):
         scale = r.grad.abs().max()
         assert scale > 0 and (o.grad - r.grad).abs().max() < 2e-3 * scale
+
+
+def test_fundamental_table_rejects_missing_pairs():
+    """lib/core/loss.py:123 indexes {(subject, a, b): F} and raises KeyError on a missing pair; a table that
+    zero-filled it would silently shrink the loss."""
+    from pose_unsupervised_b200.core.loss import FundamentalTable, epipolar_residuals
+    rigs = synth.camera_table(2, 4, seed=3)
+    F = oepi.fundamental_table({s: rigs[s] for s in range(2)})
+    FundamentalTable(F, 4)                                  # complete: fine
+    broken = dict(F)
+    del broken[(1, 2, 0)]
+    with pytest.raises(KeyError):
+        FundamentalTable(broken, 4)
+    with pytest.raises(ValueError):
+        epipolar_residuals(np.zeros((7, 17, 2)), np.zeros(1, dtype=np.int64), F)      # 7 rows, 4 views

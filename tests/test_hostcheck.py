@@ -188,3 +188,27 @@ def test_plumb_bob_and_undistort_vs_oracle(hc):
             out = np.zeros((50, 2))
             hc.hc_undistort(P(pk), nd, P(uv), 50, P(out))
             assert np.abs(out - system._cams['c'].undistort(uv)).max() < 1e-9
+
+
+def test_device_plumb_bob_vs_cv2_projectPoints(hc):
+    """The kernels' forward model (csrc/lift_math.cuh::project_plumb_bob, compiled for the host) against
+    OpenCV's own projectPoints: an anchor that does not go through the oracle's restatement at all."""
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(31)
+    worst = 0.0
+    for seed in range(4):
+        rig = synth.camera_ring(4, seed=80 + seed)
+        pts = np.ascontiguousarray(rng.normal(0, 700, (100, 3)) + [0, 0, 900.0])
+        for cam in rig:
+            R = np.asarray(cam['R'], dtype=np.float64)
+            rvec, _ = cv2.Rodrigues(R)
+            tvec = -R.dot(np.asarray(cam['T'], dtype=np.float64).reshape(3, 1))
+            K = np.array([[cam['fx'][0], 0, cam['cx'][0]], [0, cam['fy'][0], cam['cy'][0]], [0, 0, 1.0]])
+            D = np.array([cam['k'][0, 0], cam['k'][1, 0], cam['p'][0, 0], cam['p'][1, 0], cam['k'][2, 0]])
+            pk = pack_camera(cam)
+            for model, dist in ((1, D), (2, np.zeros(5))):
+                out = np.zeros((100, 2))
+                hc.hc_project(P(pk), P(pts), 100, model, P(out))
+                ref, _ = cv2.projectPoints(pts.reshape(-1, 1, 3), rvec, tvec, K, dist)
+                worst = max(worst, np.abs(out - ref.reshape(-1, 2)).max())
+    assert worst < 1e-8

@@ -267,3 +267,91 @@ def test_bilinear_restatement_vs_scipy_rgi_random():
         ref = rgi(xy)
         got = opict.bilinear_zero_outside(hmap, xy)
         assert np.array_equal(ref, got, equal_nan=True)
+
+
+def _rvec_tvec(cam):
+    """OpenCV extrinsics of an H36M camera dict: x_c = R X + t with t = -R T (triangulate.py:31-32)."""
+    cv2 = pytest.importorskip('cv2')
+    R = np.asarray(cam['R'], dtype=np.float64)
+    rvec, _ = cv2.Rodrigues(R)
+    tvec = -R.dot(np.asarray(cam['T'], dtype=np.float64).reshape(3, 1))
+    K = np.array([[cam['fx'][0], 0, cam['cx'][0]], [0, cam['fy'][0], cam['cy'][0]], [0, 0, 1.0]])
+    D = np.array([cam['k'][0, 0], cam['k'][1, 0], cam['p'][0, 0], cam['p'][1, 0], cam['k'][2, 0]])
+    return rvec, tvec, K, D
+
+
+def test_find2d_matches_cv2_projectPoints():
+    """Independent anchor for the restated pymvg find2d (forward plumb-bob model): OpenCV's own
+    projectPoints with the same K, distortion vector [k1,k2,p1,p2,k3] and extrinsics, with and without
+    distortion, on points all over the capture volume."""
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(17)
+    worst = 0.0
+    for seed in range(4):
+        rig = synth.camera_ring(4, seed=40 + seed)
+        pts = rng.normal(0, 700, (200, 3)) + [0, 0, 900.0]
+        for v, cam in enumerate(rig):
+            rvec, tvec, K, D = _rvec_tvec(cam)
+            for nd in (False, True):
+                system = otri.build_multi_camera_system([('c', cam)], no_distortion=nd)
+                ref, _ = cv2.projectPoints(pts.reshape(-1, 1, 3), rvec, tvec, K, np.zeros(5) if nd else D)
+                got = np.array([system.find2d('c', p) for p in pts])
+                worst = max(worst, np.abs(got - ref.reshape(-1, 2)).max())
+    assert worst < 1e-8                                                        # px
+
+
+@pytest.mark.parametrize('nviews', [3, 4, 8])
+def test_n_view_find3d_matches_eigh_and_gesvd(nviews):
+    """Independent anchors for the restated find3d beyond two views: the null vector of the stacked DLT
+    rows from (a) numpy's symmetric eigen-solver on A^T A and (b) LAPACK's QR-iteration SVD (gesvd), a
+    different algorithm from the divide-and-conquer gesdd behind np.linalg.svd."""
+    import scipy.linalg
+    rig = synth.camera_ring(nviews, seed=60 + nviews)
+    poses = synth.random_poses(6, seed=61)
+    obs, cams = synth.multiview_observations(poses, [rig], [0] * 6, noise_px=2.0, seed=62)
+    system = otri.build_multi_camera_system([('camera_%d' % v, rig[v]) for v in range(nviews)])
+    worst_eigh = worst_svd = 0.0
+    for f in range(6):
+        for j in range(17):
+            pts = [('camera_%d' % v, obs[f * nviews + v, j]) for v in range(nviews)]
+            got = system.find3d(pts)
+            rows = []
+            for name, xy in pts:
+                cam = system._cams[name]
+                x, y = cam.undistort(np.asarray(xy).reshape(1, 2))[0]
+                rows += [x * cam.M[2] - cam.M[0], y * cam.M[2] - cam.M[1]]
+            A = np.array(rows)
+            w, vecs = np.linalg.eigh(A.T.dot(A))
+            e = vecs[:, 0]
+            worst_eigh = max(worst_eigh, np.linalg.norm(got - e[:3] / e[3]))
+            _, _, vt = scipy.linalg.svd(A, lapack_driver='gesvd')
+            worst_svd = max(worst_svd, np.linalg.norm(got - vt[-1, :3] / vt[-1, 3]))
+    assert worst_svd < 1e-6 and worst_eigh < 1e-4                              # mm (eigh squares the condition number)
+
+
+def test_load_camera_from_M_normalises_a_scaled_projection_matrix():
+    """pymvg's load_camera_from_M divides by K[2,2] when the projection matrix arrives scaled
+    (M -> a M): K, R, t, the projections and the triangulated points must not depend on the scale."""
+    rng = np.random.default_rng(23)
+    cam = synth.camera_ring(4, seed=70)[1]
+    base = otri.build_multi_camera_system([('c', cam)])._cams['c']
+    pts = rng.normal(0, 500, (20, 3)) + [0, 0, 900.0]
+    from oracle.pymvg_restated import RestatedCamera, RestatedMultiCameraSystem
+    for scale in (2.5, 0.01, -3.0, 1.0 + 1e-9):
+        cam2 = RestatedCamera.load_camera_from_M(base.M * scale, name='c', distortion_coefficients=base.D)
+        assert abs(cam2.K[2, 2] - 1.0) < 1e-12
+        assert np.abs(cam2.K - base.K).max() < 1e-7 * np.abs(base.K).max()
+        assert np.abs(cam2.R - base.R).max() < 1e-10
+        assert np.abs(cam2.project_3d_to_pixel(pts) - base.project_3d_to_pixel(pts)).max() < 1e-7
+    # and a two-camera rig built from scaled matrices triangulates to the same points
+    rig = synth.camera_ring(4, seed=71)
+    sys1 = otri.build_multi_camera_system([('camera_%d' % v, rig[v]) for v in range(4)])
+    cams2 = [RestatedCamera.load_camera_from_M(sys1._cams['camera_%d' % v].M * (1.7 + v), name='camera_%d' % v,
+                                               distortion_coefficients=sys1._cams['camera_%d' % v].D) for v in range(4)]
+    sys2 = RestatedMultiCameraSystem(cams2)
+    X = np.array([120.0, -80.0, 1000.0])
+    obs = [('camera_%d' % v, sys1.find2d('camera_%d' % v, X)) for v in range(4)]
+    assert np.linalg.norm(sys1.find3d(obs) - X) < 1e-6
+    # the DLT rows scale with M, so the minimiser under noise does depend on the scale -- which is why the
+    # product keeps the reference's K[2,2] = 1 construction (triangulate.py:29-36); noise-free it does not
+    assert np.linalg.norm(sys2.find3d(obs) - X) < 1e-6
