@@ -347,8 +347,9 @@ def run_ours(args):
     gt = torch.zeros((B, J, 3), dtype=torch.float64, device=dev)   # MPJPE reference for the exchange step
     nframes_total = B * world
     # exchange step: ONE all-gather of [3D poses | MPJPE partial sums]; the lift kernel writes the
-    # poses straight into the send buffer.  Two slots: the all-gather of step k-1 overlaps step k.
-    nslots = 2 if world > 1 else 1
+    # poses straight into the send buffer.  Four slots: the all-gather of step k-1 overlaps step k and is only
+    # waited for when its slot comes round again, three steps later.
+    nslots = 4 if world > 1 else 1
     exch = parallel.PoseExchange(nframes_total, J, dev, nslots=nslots)
 
     def compute(slot, fork=None, ev=None):
@@ -363,8 +364,8 @@ def run_ours(args):
         mpjpe_stats(res.poses3d, gt, out=exch.stats_view(slot))
         return res
 
-    def step(k, ev=None):
-        return exch.pipelined_step(k, lambda slot, fork: compute(slot, fork if world > 1 else None, ev))
+    def step(k, ev=None, join=True):
+        return exch.pipelined_step(k, lambda slot, fork: compute(slot, fork if world > 1 else None, ev), join=join)
 
     def fence():
         if world > 1:
@@ -375,31 +376,52 @@ def run_ours(args):
         step(k)
     fence()
 
-    # One CUDA graph per slot holds the whole step (4 kernels, a memset and -- forked onto the side
-    # stream at the graph's root -- the NCCL all-gather of the other slot): at ~0.7 ms per step the
-    # Python/launch overhead of the eager path is otherwise visible, above all at N > 1.
-    graphs, graphed = [], False
-    run_step = step
+    # CUDA graphs hold the steps (4 kernels and a memset each and -- forked onto the side stream after the
+    # decode -- the NCCL all-gather of the other slot): at ~0.7 ms per step the Python/launch overhead of the
+    # eager path is otherwise visible, above all at N > 1.  One graph spans GRAPH_STEPS steps so that only its
+    # last all-gather is joined at the graph's end; the others are joined one step later, where their slot is
+    # reused, and never wait.
+    GRAPH_STEPS = 8 if world > 1 else 1
+    graphs, graphed = {}, False
+
+    def capture(nsteps):
+        gph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gph):
+            for k in range(nsteps):
+                step(k, join=False)
+            exch.join()
+        return gph
+
+    def run_steps(nsteps):
+        """nsteps steps starting at slot 0 (nsteps is even or the last block): graph replays when captured."""
+        if not graphed:
+            for k in range(nsteps):
+                step(k, join=False)
+            exch.join()
+            return
+        full, rest = divmod(nsteps, GRAPH_STEPS)
+        for _ in range(full):
+            graphs[GRAPH_STEPS].replay()
+        if rest:
+            graphs[rest].replay()
+
     if not args.no_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for k in range(nslots):
+                for k in range(2 * nslots):
                     step(k)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            for k in range(nslots):
-                gph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gph):
-                    step(k)
-                graphs.append(gph)
-            run_step, graphed = (lambda k: graphs[k % nslots].replay()), True
-            for k in range(2 * nslots):
-                run_step(k)
+            graphs[GRAPH_STEPS] = capture(GRAPH_STEPS)
+            if steps % GRAPH_STEPS:
+                graphs[steps % GRAPH_STEPS] = capture(steps % GRAPH_STEPS)
+            graphed = True
+            run_steps(2 * GRAPH_STEPS)
         except Exception as e:   # fall back to eager launches, say so in the JSON line
             sys.stderr.write('CUDA graph capture failed (%s); timing eager launches\n' % e)
-            graphs, run_step, graphed = [], step, False
+            graphs, graphed = {}, False
     fence()
 
     clocks = ClockSampler(local)
@@ -407,9 +429,8 @@ def run_ours(args):
     clocks.start()
     fence()
     start.record()
-    for i in range(steps):
-        run_step(i)
-    last_slot = (steps - 1) % nslots
+    run_steps(steps)
+    last_slot = (steps - 1) % GRAPH_STEPS % nslots if steps % GRAPH_STEPS else (GRAPH_STEPS - 1) % nslots
     if world > 1:
         exch.run(last_slot)                 # drain: the last step's exchange is inside the timed region
     stop.record()
@@ -454,9 +475,9 @@ def run_ours(args):
 
     # ---- end to end through the public numpy API, host buffers ------------------------------
     e2e_steps = max(1, min(3, steps))
-    pinned = torch.empty((B * V, J, HW, HW), dtype=torch.float32, pin_memory=True)
-    pinned.copy_(hm)
-    torch.cuda.synchronize()
+    e2e_value = e2e_same = None
+    h2d = d2h = 0
+    e2e_pageable = None
 
     def e2e_run(host_hm):
         lift_heatmaps(host_hm, center, scale, table, nviews=V, post_process=True).numpy()   # warm-up
@@ -468,20 +489,23 @@ def run_ours(args):
         dt = parallel.max_over_ranks(time.perf_counter() - t0, dev)
         return nframes_total * e2e_steps / dt, out
 
-    e2e_value, out = e2e_run(pinned.numpy())           # numpy view of pinned memory
-    d2h = sum(a.nbytes for a in (out.xy, out.maxvals, out.poses3d, out.reproj_err))
-    h2d = pinned.numel() * 4 + center.nbytes + scale.nbytes
-    e2e_same = bool(np.array_equal(out.poses3d, own_poses.cpu().numpy()))
-    e2e_pageable = None
-    if not args.no_pageable:
-        pageable = np.empty(tuple(pinned.shape), dtype=np.float32)     # plain malloc'ed host memory
-        np.copyto(pageable, pinned.numpy())
-        pv, pout = e2e_run(pageable)
-        e2e_pageable = {'value': pv, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                        'steps': e2e_steps, 'equals_pinned_result': bool(np.array_equal(pout.poses3d, out.poses3d)),
-                        'note': 'pageable numpy input staged through two pinned buffers in 256 MiB chunks'}
-        del pageable
-    del pinned
+    if not args.no_e2e:
+        pinned = torch.empty((B * V, J, HW, HW), dtype=torch.float32, pin_memory=True)
+        pinned.copy_(hm)
+        torch.cuda.synchronize()
+        e2e_value, out = e2e_run(pinned.numpy())           # numpy view of pinned memory
+        d2h = sum(a.nbytes for a in (out.xy, out.maxvals, out.poses3d, out.reproj_err))
+        h2d = pinned.numel() * 4 + center.nbytes + scale.nbytes
+        e2e_same = bool(np.array_equal(out.poses3d, own_poses.cpu().numpy()))
+        if not args.no_pageable:
+            pageable = np.empty(tuple(pinned.shape), dtype=np.float32)     # plain malloc'ed host memory
+            np.copyto(pageable, pinned.numpy())
+            pv, pout = e2e_run(pageable)
+            e2e_pageable = {'value': pv, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                            'steps': e2e_steps, 'equals_pinned_result': bool(np.array_equal(pout.poses3d, out.poses3d)),
+                            'note': 'pageable numpy input staged through two pinned buffers in 256 MiB chunks'}
+            del pageable
+        del pinned
 
     line = None
     if rank == 0:
@@ -491,13 +515,13 @@ def run_ours(args):
             'metric': metric_name(), 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': steps,
             'warmup': warmup, 'ms_per_step': ms_total / steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 decode, f64 lift', 'data': 'synthetic',
-            'config': dict(workload_config(B), cuda_graph=graphed,
+            'config': dict(workload_config(B), cuda_graph=graphed, steps_per_graph=GRAPH_STEPS if graphed else None,
                            exchange='none (1 GPU)' if world == 1 else
                            'one ncclAllGather of [poses | MPJPE sums] per step, double-buffered: the gather of '
-                           'step k-1 is forked onto a side stream after the decode of step k and runs under its lift / '
-                           'MPJPE kernels; the last one is drained inside the timed region'),
+                           'step k-1 is forked onto a side stream after the decode of step k, runs under its lift / MPJPE '
+                           'kernels and is joined one step later; the last one is drained inside the timed region'),
             'clocks': clock_info,
-            'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d),
+            'e2e': None if args.no_e2e else {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps, 'host_memory': 'pinned',
                     'equals_device_resident_result': e2e_same,
                     'api': 'pose_unsupervised_b200.multiviews.triangulate.lift_heatmaps (numpy in, numpy out)'},
@@ -528,7 +552,7 @@ def run_ours(args):
 
     # drop everything that captured a collective before the group goes away (NCCL's teardown waits
     # for CUDA graphs that hold its kernels)
-    graphs, run_step = None, None
+    graphs = None
     gc.collect()
     torch.cuda.synchronize()
 
@@ -891,6 +915,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-secondary', action='store_true', help='skip the RPSM / pseudo-label / sweep legs of the default run')
     ap.add_argument('--no-pageable', action='store_true', help='skip the pageable-memory e2e leg')
+    ap.add_argument('--no-e2e', action='store_true', help='sweep runs only: skip the host-buffer legs (e2e is then null)')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA graph replay')
     args = ap.parse_args()
     global V, J, HW

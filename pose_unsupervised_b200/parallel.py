@@ -84,6 +84,8 @@ class PoseExchange(object):
         self.send = [torch.zeros(self.width, dtype=dtype, device=device) for _ in range(nslots)]
         self.recv = [torch.zeros(self.world * self.width, dtype=dtype, device=device) for _ in range(nslots)]
         self.side = torch.cuda.Stream(device=device) if (device.type == 'cuda' and nslots > 1) else None
+        self._pending = False     # a collective forked onto the side stream has not been joined yet
+        self._gathered = [None] * nslots   # per slot: event of the un-joined collective that reads it
 
     def poses_view(self, slot=0):
         b = self.counts[self.rank]
@@ -99,13 +101,18 @@ class PoseExchange(object):
         else:
             self.recv[slot].copy_(self.send[slot])
 
-    def pipelined_step(self, k, compute):
-        """Step ``k`` of a double-buffered loop: ``compute(slot, fork)`` fills slot ``k % nslots`` on the
+    def pipelined_step(self, k, compute, join=True):
+        """Step ``k`` of a multi-buffered loop: ``compute(slot, fork)`` fills slot ``k % nslots`` on the
         current stream; the all-gather of the previous step's slot runs on the side stream from the
         moment ``compute`` calls ``fork()`` (at the latest when it returns).  Forking after the
         HBM-bound decode and before the small latency-bound kernels puts the collective where SMs are
-        idle.  Fork and join are stream waits, so the step is capturable in a CUDA graph (one graph
-        per slot).  The last step's slot is still to be gathered afterwards: ``run((K-1) % nslots)``.
+        idle.  With ``join=True`` the current stream waits for the collective at the end of the step.
+        With ``join=False`` the wait moves to the ``fork()`` of the step that REUSES the slot the
+        collective reads (``nslots - 1`` steps later), so ranks may drift apart by that many steps before
+        anybody waits; call ``join()`` after the last step of a block (required before the end of a
+        CUDA-graph capture).  Fork and join are stream / event waits, so any number of steps is
+        capturable in one CUDA graph.  The last step's slot is still to be gathered afterwards:
+        ``run((K-1) % nslots)``.
         """
         cur, prev = k % self.nslots, (k - 1) % self.nslots
         if self.world == 1:
@@ -120,15 +127,30 @@ class PoseExchange(object):
             if self.side is None:                   # CPU tensors (gloo tests): same order, no overlap
                 self.run(prev)
                 return
+            done = self._gathered[cur]
+            if done is not None:
+                main.wait_event(done)               # the collective that read slot `cur` has finished
+                self._gathered[cur] = None
             self.side.wait_stream(main)             # everything issued so far, step k-1 included, is ahead
             with torch.cuda.stream(self.side):
                 self.run(prev)
+                ev = torch.cuda.Event()
+                ev.record(self.side)
+            self._gathered[prev] = ev
+            self._pending = True
 
         out = compute(cur, fork)
         fork()
-        if self.side is not None:
-            main.wait_stream(self.side)             # join
+        if join:
+            self.join()
         return out
+
+    def join(self):
+        """The current stream waits for every collective in flight on the side stream."""
+        if self.side is not None and self.world > 1 and self._pending:
+            torch.cuda.current_stream().wait_stream(self.side)
+        self._pending = False
+        self._gathered = [None] * self.nslots
 
     def gathered_poses(self, slot=0):
         rows = self.recv[slot].view(self.world, self.width)
