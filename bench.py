@@ -334,6 +334,10 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+    # measured (profiles/r02_scaling.md): at 2 GPUs the all-gather ends before the next decode starts and static
+    # striding is 1.5 % faster; at 8 GPUs it spills into the next decode and dynamic claims are 2.3 % faster
+    dynamic = args.decode_schedule == 'dynamic' or (args.decode_schedule == 'auto' and world >= 4)
+    rt.set_decode_schedule(dynamic)
     steps = args.steps if args.steps else 200
     warmup = args.warmup if args.warmup is not None else 10
     warmup = max(warmup, 3)
@@ -515,7 +519,7 @@ def run_ours(args):
             'metric': metric_name(), 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': steps,
             'warmup': warmup, 'ms_per_step': ms_total / steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 decode, f64 lift', 'data': 'synthetic',
-            'config': dict(workload_config(B), cuda_graph=graphed, steps_per_graph=GRAPH_STEPS if graphed else None,
+            'config': dict(workload_config(B), decode_schedule='dynamic' if dynamic else 'static', cuda_graph=graphed, steps_per_graph=GRAPH_STEPS if graphed else None,
                            exchange='none (1 GPU)' if world == 1 else
                            'one ncclAllGather of [poses | MPJPE sums] per step, double-buffered: the gather of '
                            'step k-1 is forked onto a side stream after the decode of step k, runs under its lift / MPJPE '
@@ -916,6 +920,8 @@ def main():
     ap.add_argument('--no-secondary', action='store_true', help='skip the RPSM / pseudo-label / sweep legs of the default run')
     ap.add_argument('--no-pageable', action='store_true', help='skip the pageable-memory e2e leg')
     ap.add_argument('--no-e2e', action='store_true', help='sweep runs only: skip the host-buffer legs (e2e is then null)')
+    ap.add_argument('--decode-schedule', default='auto', choices=['auto', 'static', 'dynamic'],
+                    help='auto = dynamic map claims when the exchange spills into the next decode (N >= 4), static otherwise')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA graph replay')
     args = ap.parse_args()
     global V, J, HW

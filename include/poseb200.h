@@ -71,6 +71,20 @@ int pb200_crop_affine(const void* center, int center_dtype, const void* scale, i
                       const double* rot_sincos, double shift_x, double shift_y, int shift_dtype,
                       int n, int out_w, int out_h, int inv, double* out, void* stream);
 
+/* ---- tuning (process-wide) --------------------------------------------------------
+ * PB200_TUNE_DECODE_SCHEDULE: how the persistent decode kernel hands maps to its warps.
+ *   PB200_DECODE_STATIC  (default) warp w of block b takes maps b*8+w, +grid*8, ...: fastest when the
+ *                        decode has the GPU to itself.
+ *   PB200_DECODE_DYNAMIC warps claim batches of maps from a counter: a block that starts late because
+ *                        another kernel (an overlapped NCCL collective) still holds its SM decodes fewer
+ *                        maps instead of finishing late.  The library keeps a 32 KiB pool of claim counters
+ *                        per device for this (allocated on first use).  Results are identical.
+ */
+#define PB200_TUNE_DECODE_SCHEDULE 2
+#define PB200_DECODE_STATIC 0
+#define PB200_DECODE_DYNAMIC 1
+int pb200_set_tuning(int key, int value);
+
 /* ---- heatmap decode ---------------------------------------------------------------
  * Replaces core.inference.get_max_preds (lib/core/inference.py:19-47) when
  * affine == NULL and core.inference.get_final_preds (:50-75) otherwise.

@@ -14,6 +14,7 @@ F32, F64 = 0, 1
 MAX_VIEWS = 8
 CAM_STRIDE = 24
 RPSM_MAX_JOINTS = 32
+TUNE_DECODE_SCHEDULE, DECODE_STATIC, DECODE_DYNAMIC = 2, 0, 1
 
 
 class Pb200Error(RuntimeError):
@@ -25,6 +26,7 @@ _PROTOS = {
     'pb200_last_error': (c_char_p, []),
     'pb200_device_check': (c_int, []),
     'pb200_sm_count': (c_int, []),
+    'pb200_set_tuning': (c_int, [c_int, c_int]),
     'pb200_crop_affine': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_double, c_double, c_int,
                                   c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'pb200_decode': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,

@@ -9,6 +9,9 @@
 namespace pb200 {
 
 constexpr int kDecodeWarps = 8;
+// PB200_TUNE_DECODE_SCHEDULE (pb200_set_tuning): static striding when the decode has the GPU to itself;
+// dynamic claims win when something else holds SMs while it starts (profiles/r02_scaling.md)
+static int g_decode_schedule = PB200_DECODE_STATIC;
 
 __global__ void __launch_bounds__(kDecodeWarps * 32)
 decode_kernel(HmViews hv, int N, int J, int H, int W, int vec_ok,
@@ -34,24 +37,52 @@ decode_kernel(HmViews hv, int N, int J, int H, int W, int vec_ok,
   }
 }
 
-// Same decode with the TMA ring front end (decode.cuh::stream_maps_tma); warps take maps
-// blockIdx*8+warp, +gridDim*8, ... so no claim counter is needed.
+// Same decode with the TMA ring front end (decode.cuh::stream_maps_tma).
+//   claim_ctr == nullptr : warps take maps blockIdx*8+warp, +gridDim*8, ... (static)
+//   claim_ctr != nullptr : warps pull BATCHES of map indices from claim_ctr[0] (dynamic, guided: 8 maps
+//     per claim while there is plenty left, down to 1 at the very end -- same-address atomics are served
+//     at ~0.2 per ns on B200, one claim per map would saturate that and cost 50 %).  Every warp keeps
+//     one claim in flight -- the atomic for its next batch is issued when the current batch is opened,
+//     long before its result is needed -- so the round trip never stalls the stream.  A block that starts
+//     late (because another kernel, e.g. an NCCL collective overlapping the start of the step, still holds
+//     its SM) then simply decodes fewer maps instead of finishing late.  The last block out
+//     (claim_ctr[1] counts them) zeroes both words, so the pair is clean for the next launch.
 #ifndef PB_DECODE_MIN_BLOCKS
 #define PB_DECODE_MIN_BLOCKS 2
 #endif
 __global__ void __launch_bounds__(kDecodeWarps * 32, PB_DECODE_MIN_BLOCKS)
 decode_tma_kernel(HmViews hv, int N, int J, int H, int W, const double* __restrict__ affine,
                   int post_process, float* __restrict__ out_xy, float* __restrict__ out_maxval,
-                  int32_t* __restrict__ out_idx) {
+                  int32_t* __restrict__ out_idx, int* __restrict__ claim_ctr) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long total_ll = (long long)N * J;
   const int total = (int)total_ll;
   const long long stride = (long long)gridDim.x * kDecodeWarps;
   long long next = (long long)blockIdx.x * kDecodeWarps + warp;
+  // dynamic form: [cur_m, cur_end) is the open batch (warp-uniform); ahead_m0 (lane 0) / ahead_b describe
+  // the batch claimed ahead of time
+  // the batch claimed ahead of time.  The FIRST batch of every warp is fixed (maps 8w .. 8w+7 of global warp
+  // w; the counter hands out what comes after those): no warp has to wait for an atomic before it can start,
+  // and the 2368 first claims, which arrive all at once, have a whole batch of time to be served.
+  const int nwarps_total = (int)gridDim.x * kDecodeWarps;
+  const int first_free = nwarps_total * 8;
+  int cur_m = (blockIdx.x * kDecodeWarps + warp) * 8, cur_end = cur_m + 8, ahead_m0 = 0, ahead_b = 8;
+  if (claim_ctr != nullptr && lane == 0) ahead_m0 = atomicAdd(claim_ctr, ahead_b) + first_free;
   stream_maps_tma(
       smem_raw, kDecodeWarps, hv, J, H, W, total, affine, post_process != 0,
       [&]() {
+        if (claim_ctr != nullptr) {
+          if (cur_m >= cur_end) {   // open the batch claimed earlier, claim the one after it
+            cur_m = __shfl_sync(0xffffffffu, ahead_m0, 0);
+            cur_end = cur_m + ahead_b;
+            const int left = total - cur_end;
+            ahead_b = left <= 0 ? 1 : min(8, max(1, left / (3 * nwarps_total)));
+            if (lane == 0) ahead_m0 = atomicAdd(claim_ctr, ahead_b) + first_free;
+          }
+          const int m = cur_m++;
+          return m < total ? m : total;
+        }
         const long long m = next;
         next += stride;
         return m < total_ll ? (int)m : total;
@@ -65,7 +96,49 @@ decode_tma_kernel(HmViews hv, int N, int J, int H, int W, const double* __restri
         return 0;
       },
       [&](int, int) {});
+  if (claim_ctr != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(claim_ctr + 1, 1) == (int)gridDim.x - 1) {
+      claim_ctr[0] = 0;
+      claim_ctr[1] = 0;
+    }
+  }
 }
+
+// ---- claim counters for the dynamic form -----------------------------------------------------------
+// A pool of (counter, blocks-done) pairs per device, zeroed once; every launch takes its own pair, so
+// launches that overlap on different streams never share one: eager launches cycle through the first half
+// (a pair is back to zero long before it comes round again), launches recorded into a CUDA graph take a
+// pair of the second half for good (a graph cannot run concurrently with itself).  No pair left, or the
+// pool not yet allocated while a capture is in progress -> the static form, same results.
+namespace {
+constexpr int kClaimPairs = 4096;
+struct ClaimPool {
+  int* dev;
+  unsigned eager, captured;
+};
+int* take_claim_pair(cudaStream_t stream) {
+  static PerDevice<ClaimPool> pools;
+  ClaimPool* pool = pools.slot();
+  if (pool == nullptr) return nullptr;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  const bool capturing = st != cudaStreamCaptureStatusNone;
+  if (pool->dev == nullptr) {
+    if (capturing) return nullptr;                       // cannot zero the pool inside a capture
+    int* d = nullptr;
+    if (cudaMalloc(&d, sizeof(int) * 2 * kClaimPairs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemset(d, 0, sizeof(int) * 2 * kClaimPairs) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
+    pool->dev = d;                                       // 32 KiB per device, kept for the life of the process
+  }
+  if (capturing) {
+    const unsigned k = __sync_fetch_and_add(&pool->captured, 1u);
+    if (k >= (unsigned)kClaimPairs / 2) return nullptr;
+    return pool->dev + 2 * (kClaimPairs / 2 + k);
+  }
+  return pool->dev + 2 * (__sync_fetch_and_add(&pool->eager, 1u) % (kClaimPairs / 2));
+}
+}  // namespace
 
 __global__ void crop_affine_kernel(const void* center, int c_f64, const void* scale, int s_f64,
                                    const double* __restrict__ rot_sincos, double shift_x, double shift_y,
@@ -102,6 +175,13 @@ bool views_vec_ok(const HmViews& hv, int HW) {
 }  // namespace pb200
 
 using namespace pb200;
+
+extern "C" int pb200_set_tuning(int key, int value) {
+  PB_REQUIRE(key == PB200_TUNE_DECODE_SCHEDULE, "unknown tuning key %d", key);
+  PB_REQUIRE(value == PB200_DECODE_STATIC || value == PB200_DECODE_DYNAMIC, "decode schedule must be 0 (static) or 1 (dynamic)");
+  pb200::g_decode_schedule = value;
+  return PB200_OK;
+}
 
 extern "C" int pb200_crop_affine(const void* center, int center_dtype, const void* scale,
                                  int scale_dtype, const double* rot_sincos, double shift_x,
@@ -158,8 +238,10 @@ int pb200::launch_decode(const HmViews& hv, int N, int J, int H, int W, const do
     long long blocks = (maps + kDecodeWarps - 1) / kDecodeWarps;
     const long long cap = (long long)sm * *per_sm;
     if (blocks > cap) blocks = cap;
+    // dynamic claims only when the grid is the full persistent wave (otherwise every warp has one map)
+    int* claim = (blocks == cap && g_decode_schedule == PB200_DECODE_DYNAMIC) ? take_claim_pair((cudaStream_t)stream) : nullptr;
     decode_tma_kernel<<<(unsigned)blocks, kDecodeWarps * 32, smem, (cudaStream_t)stream>>>(
-        hv, N, J, H, W, affine, post_process, out_xy, out_maxval, out_idx);
+        hv, N, J, H, W, affine, post_process, out_xy, out_maxval, out_idx, claim);
     PB_LAUNCH_CHECK("decode_tma_kernel");
     return PB200_OK;
   }

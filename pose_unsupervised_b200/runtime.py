@@ -111,3 +111,11 @@ def to_host(t, like=None):
     if like is not None and a.dtype != like:
         a = a.astype(like)
     return a
+
+
+def set_decode_schedule(dynamic):
+    """Process-wide: let the decode kernel's warps claim their maps dynamically (use it when a collective
+    or another kernel overlaps the start of the decode, see parallel.PoseExchange) or by static striding
+    (default; 2.5 % faster when the decode runs alone).  Results are identical."""
+    _lib.call('pb200_set_tuning', _lib.TUNE_DECODE_SCHEDULE,
+              _lib.DECODE_DYNAMIC if dynamic else _lib.DECODE_STATIC)
