@@ -39,14 +39,12 @@ decode_kernel(HmViews hv, int N, int J, int H, int W, int vec_ok,
 
 // Same decode with the TMA ring front end (decode.cuh::stream_maps_tma).
 //   claim_ctr == nullptr : warps take maps blockIdx*8+warp, +gridDim*8, ... (static)
-//   claim_ctr != nullptr : warps pull BATCHES of map indices from claim_ctr[0] (dynamic, guided: 8 maps
-//     per claim while there is plenty left, down to 1 at the very end -- same-address atomics are served
-//     at ~0.2 per ns on B200, one claim per map would saturate that and cost 50 %).  Every warp keeps
-//     one claim in flight -- the atomic for its next batch is issued when the current batch is opened,
-//     long before its result is needed -- so the round trip never stalls the stream.  A block that starts
-//     late (because another kernel, e.g. an NCCL collective overlapping the start of the step, still holds
-//     its SM) then simply decodes fewer maps instead of finishing late.  The last block out
-//     (claim_ctr[1] counts them) zeroes both words, so the pair is clean for the next launch.
+//   claim_ctr != nullptr : after a fixed strided share, warps pull small BATCHES of map indices from
+//     claim_ctr[0] (same-address atomics are served at ~0.2 per ns on B200: one claim per map for the whole
+//     kernel would saturate that and cost 50 %).  A block that starts late (because another kernel, e.g. an
+//     NCCL collective overlapping the start of the step, still holds its SM) then simply decodes fewer maps
+//     instead of finishing late.  The last block out (claim_ctr[1] counts them) zeroes both words, so the pair
+//     is clean for the next launch.
 #ifndef PB_DECODE_MIN_BLOCKS
 #define PB_DECODE_MIN_BLOCKS 2
 #endif
@@ -60,24 +58,28 @@ decode_tma_kernel(HmViews hv, int N, int J, int H, int W, const double* __restri
   const int total = (int)total_ll;
   const long long stride = (long long)gridDim.x * kDecodeWarps;
   long long next = (long long)blockIdx.x * kDecodeWarps + warp;
-  // dynamic form: [cur_m, cur_end) is the open batch (warp-uniform); ahead_m0 (lane 0) / ahead_b describe
-  // the batch claimed ahead of time
-  // the batch claimed ahead of time.  The FIRST batch of every warp is fixed (maps 8w .. 8w+7 of global warp
-  // w; the counter hands out what comes after those): no warp has to wait for an atomic before it can start,
-  // and the 2368 first claims, which arrive all at once, have a whole batch of time to be served.
+  // dynamic form: every warp first takes a FIXED, strided share (7/8 of an even split: map w + k * nwarps, the
+  // same interleaving as the static form) and only the rest comes from the counter, in small batches:
+  // [cur_m, cur_end) is the open batch (warp-uniform), ahead_m0 (lane 0) / ahead_b the batch claimed ahead of
+  // time -- its atomic is issued when the previous batch is opened (the first one at kernel start), so no warp
+  // ever waits for a round trip.  A block that starts up to ~1/8 of the kernel's duration late is absorbed.
   const int nwarps_total = (int)gridDim.x * kDecodeWarps;
-  const int first_free = nwarps_total * 8;
-  int cur_m = (blockIdx.x * kDecodeWarps + warp) * 8, cur_end = cur_m + 8, ahead_m0 = 0, ahead_b = 8;
+  const int my_warp = (int)blockIdx.x * kDecodeWarps + warp;
+  const int fixed_per_warp = (int)((total_ll / nwarps_total) * 7 / 8);
+  const int first_free = fixed_per_warp * nwarps_total;
+  int k_fixed = 0, cur_m = 0, cur_end = 0, ahead_m0 = 0;
+  int ahead_b = min(4, max(1, (total - first_free) / nwarps_total));
   if (claim_ctr != nullptr && lane == 0) ahead_m0 = atomicAdd(claim_ctr, ahead_b) + first_free;
   stream_maps_tma(
       smem_raw, kDecodeWarps, hv, J, H, W, total, affine, post_process != 0,
       [&]() {
         if (claim_ctr != nullptr) {
+          if (k_fixed < fixed_per_warp) return my_warp + (k_fixed++) * nwarps_total;
           if (cur_m >= cur_end) {   // open the batch claimed earlier, claim the one after it
             cur_m = __shfl_sync(0xffffffffu, ahead_m0, 0);
             cur_end = cur_m + ahead_b;
             const int left = total - cur_end;
-            ahead_b = left <= 0 ? 1 : min(8, max(1, left / (3 * nwarps_total)));
+            ahead_b = left <= 0 ? 1 : min(4, max(1, left / nwarps_total));
             if (lane == 0) ahead_m0 = atomicAdd(claim_ctr, ahead_b) + first_free;
           }
           const int m = cur_m++;
