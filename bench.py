@@ -334,9 +334,7 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    # measured (profiles/r02_scaling.md): at 2 GPUs the all-gather ends before the next decode starts and static
-    # striding is 1.5 % faster; at 8 GPUs it spills into the next decode and dynamic claims are 2.3 % faster
-    dynamic = args.decode_schedule == 'dynamic' or (args.decode_schedule == 'auto' and world >= 4)
+    dynamic = args.decode_schedule != 'static'      # the library's default (profiles/r02_scaling.md)
     rt.set_decode_schedule(dynamic)
     steps = args.steps if args.steps else 200
     warmup = args.warmup if args.warmup is not None else 10
@@ -921,7 +919,7 @@ def main():
     ap.add_argument('--no-pageable', action='store_true', help='skip the pageable-memory e2e leg')
     ap.add_argument('--no-e2e', action='store_true', help='sweep runs only: skip the host-buffer legs (e2e is then null)')
     ap.add_argument('--decode-schedule', default='auto', choices=['auto', 'static', 'dynamic'],
-                    help='auto = dynamic map claims when the exchange spills into the next decode (N >= 4), static otherwise')
+                    help='auto = the library default (dynamic: strided share + claimed tail); static for A/B runs')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA graph replay')
     args = ap.parse_args()
     global V, J, HW

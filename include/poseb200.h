@@ -73,12 +73,14 @@ int pb200_crop_affine(const void* center, int center_dtype, const void* scale, i
 
 /* ---- tuning (process-wide) --------------------------------------------------------
  * PB200_TUNE_DECODE_SCHEDULE: how the persistent decode kernel hands maps to its warps.
- *   PB200_DECODE_STATIC  (default) warp w of block b takes maps b*8+w, +grid*8, ...: fastest when the
- *                        decode has the GPU to itself.
- *   PB200_DECODE_DYNAMIC warps claim batches of maps from a counter: a block that starts late because
- *                        another kernel (an overlapped NCCL collective) still holds its SM decodes fewer
- *                        maps instead of finishing late.  The library keeps a 32 KiB pool of claim counters
- *                        per device for this (allocated on first use).  Results are identical.
+ *   PB200_DECODE_STATIC  warp w of block b takes maps b*8+w, +grid*8, ...
+ *   PB200_DECODE_DYNAMIC (default) the same strided share for the first 7/8 of an even split, the rest claimed
+ *                        in small batches from a counter: the end of the kernel evens out (1 % faster alone)
+ *                        and a block that starts late because another kernel (an overlapped NCCL collective)
+ *                        still holds its SM decodes fewer maps instead of finishing late.  The library keeps
+ *                        a 32 KiB pool of claim counters per device for this (allocated on first use; a launch
+ *                        that finds none -- e.g. the first ever call happens inside a stream capture -- uses
+ *                        the static form).  Results are identical.
  */
 #define PB200_TUNE_DECODE_SCHEDULE 2
 #define PB200_DECODE_STATIC 0

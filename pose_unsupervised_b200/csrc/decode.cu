@@ -9,9 +9,10 @@
 namespace pb200 {
 
 constexpr int kDecodeWarps = 8;
-// PB200_TUNE_DECODE_SCHEDULE (pb200_set_tuning): static striding when the decode has the GPU to itself;
-// dynamic claims win when something else holds SMs while it starts (profiles/r02_scaling.md)
-static int g_decode_schedule = PB200_DECODE_STATIC;
+// PB200_TUNE_DECODE_SCHEDULE (pb200_set_tuning).  Dynamic (fixed strided share + claimed tail) is the default:
+// 0.639 vs 0.647 ms alone on one GPU (the claimed tail evens out the end of the kernel) and it absorbs blocks that
+// start late under an overlapped collective (profiles/r02_scaling.md)
+static int g_decode_schedule = PB200_DECODE_DYNAMIC;
 
 __global__ void __launch_bounds__(kDecodeWarps * 32)
 decode_kernel(HmViews hv, int N, int J, int H, int W, int vec_ok,

@@ -1136,7 +1136,14 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
     const double centre[3] = {p.root[3 * (size_t)f], p.root[3 * (size_t)f + 1], p.root[3 * (size_t)f + 2]};
 
     // ---- heatmap coordinates of every (bin, view), once per frame ---------------------------------
-    for (int b = tid; b < nb0; b += T) {
+    // Sampling order: slot s = tid + k*T holds bin slot_bin(s).  On the 16^3 grid the two low nibbles are
+    // swapped, so the 16 lanes of a half-warp walk along grid x instead of grid z: the vertical world axis
+    // projects to an image column, and with the 64-float pitch of a staged map the 16 taps of a column share
+    // ONE shared-memory bank; along x they spread over the banks.  The parked taps are stored by slot, so
+    // their loads stay coalesced.
+    auto slot_bin = [n0](int sl) { return n0 == 16 ? ((sl & ~0xff) | ((sl & 15) << 4) | ((sl >> 4) & 15)) : sl; };
+    for (int sl = tid; sl < nb0; sl += T) {
+      const int b = slot_bin(sl);
       double X[3];
       bin_to_point(p.grid_size, n0, b, centre, X);
       for (int v = 0; v < V; ++v) {
@@ -1144,8 +1151,8 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
         int pos;
         grid_to_heatmap(s.cam[v], s.aff[v], X, p.W, p.H, p.img_w, p.img_h, hx, hy);
         bilinear_prepare(p.W, p.H, hx, hy, pos, fx, fy);   // the joint-independent half of the sample
-        st_keep_f64x2(coords + ((size_t)v * nb0 + b) * 2, fx, fy, pol_keep);
-        st_keep_s32(tappos + (size_t)v * nb0 + b, pos, pol_keep);
+        st_keep_f64x2(coords + ((size_t)v * nb0 + sl) * 2, fx, fy, pol_keep);
+        st_keep_s32(tappos + (size_t)v * nb0 + sl, pos, pol_keep);
       }
     }
     // (every thread reads back only the coordinates it wrote itself: no barrier needed)
@@ -1165,11 +1172,11 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
               const int v0 = g * L.stage_views, v1 = min(V, v0 + L.stage_views);
 #pragma unroll
               for (int k = 0; k < kOcMaxPer; ++k) {
-                const int b = tid + k * T;
-                if (b < nb0)
+                const int sl = tid + k * T;
+                if (sl < nb0)
                   for (int v = v0; v < v1; ++v) {
-                    const double2 fr = __ldcg(reinterpret_cast<const double2*>(coords + ((size_t)v * nb0 + b) * 2));
-                    const int pos = __ldcg(tappos + (size_t)v * nb0 + b);
+                    const double2 fr = __ldcg(reinterpret_cast<const double2*>(coords + ((size_t)v * nb0 + sl) * 2));
+                    const int pos = __ldcg(tappos + (size_t)v * nb0 + sl);
                     const float* m = stage + (size_t)(v - v0) * HWm;
                     u[k] = u[k] + bilinear_apply([m](int t) { return m[t]; }, W, pos, fr.x, fr.y);
                   }
@@ -1185,11 +1192,11 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
           } else {
 #pragma unroll
             for (int k = 0; k < kOcMaxPer; ++k) {
-              const int b = tid + k * T;
-              if (b < nb0)
+              const int sl = tid + k * T;
+              if (sl < nb0)
                 for (int v = 0; v < V; ++v) {
-                  const double2 fr = __ldcg(reinterpret_cast<const double2*>(coords + ((size_t)v * nb0 + b) * 2));
-                  const int pos = __ldcg(tappos + (size_t)v * nb0 + b);
+                  const double2 fr = __ldcg(reinterpret_cast<const double2*>(coords + ((size_t)v * nb0 + sl) * 2));
+                  const int pos = __ldcg(tappos + (size_t)v * nb0 + sl);
                   const float* m = p.hm + (((size_t)f * V + v) * J + op.joint) * (size_t)HWm;
                   u[k] = u[k] + bilinear_apply([m](int t) { return __ldg(m + t); }, W, pos, fr.x, fr.y);
                 }
@@ -1197,10 +1204,10 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
           }
 #pragma unroll
           for (int k = 0; k < kOcMaxPer; ++k) {
-            const int b = tid + k * T;
-            if (b < nb0) {
+            const int sl = tid + k * T;
+            if (sl < nb0) {
               if (!(fabs(u[k]) <= 1.79769313486231570e308)) os.nonfinite = 1;   // inf / NaN: no shortcuts
-              D[b] = u[k];
+              D[slot_bin(sl)] = u[k];
             }
           }
         }

@@ -114,8 +114,8 @@ def to_host(t, like=None):
 
 
 def set_decode_schedule(dynamic):
-    """Process-wide: let the decode kernel's warps claim their maps dynamically (use it when a collective
-    or another kernel overlaps the start of the decode, see parallel.PoseExchange) or by static striding
-    (default; 2.5 % faster when the decode runs alone).  Results are identical."""
+    """Process-wide: let the decode kernel's warps claim the tail of their maps dynamically (default: it
+    evens out the end of the kernel and absorbs blocks that start late under an overlapped collective, see
+    parallel.PoseExchange) or use pure static striding.  Results are identical."""
     _lib.call('pb200_set_tuning', _lib.TUNE_DECODE_SCHEDULE,
               _lib.DECODE_DYNAMIC if dynamic else _lib.DECODE_STATIC)
