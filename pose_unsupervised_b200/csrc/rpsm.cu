@@ -1029,7 +1029,14 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
   __syncthreads();
   if (tid == 0) oc_build_program(os, J, E, p.root_idx, L.nsm + L.nspill);
   __syncthreads();
-  if (os.prog_err || os.doff[E] > L.dzm_cap) __trap();   // the host sizes both; cannot happen for a tree
+  if (os.prog_err || os.doff[E] > L.dzm_cap) {
+    // edges that do not form a tree over all joints, or a max_reach smaller than the table's real reach: the
+    // arguments are inconsistent.  Answer NaN for every frame of this block instead of corrupting memory (and
+    // instead of __trap(), which would poison the caller's CUDA context).
+    for (int f = blockIdx.x; f < p.B; f += gridDim.x)
+      for (int t = tid; t < J * 3; t += T) p.out_pose[(size_t)f * J * 3 + t] = __longlong_as_double(0x7ff8000000000000LL);
+    return;
+  }
   for (int t = tid; t < os.doff[E]; t += T) {
     int e = 0;
     while (t >= os.doff[e + 1]) ++e;

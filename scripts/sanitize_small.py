@@ -30,8 +30,8 @@ for hw in (64, 80, 17):
     hm[1, 2, 3, 4] = np.nan
     decode_heatmaps(hm)
     decode_heatmaps(hm, center, scale, post_process=True, return_idx=True)
-    for variant in (0, 1, 2):
-        _lib.call('pb200_set_tuning', 1, variant)
+    for schedule in (0, 1):
+        _lib.call('pb200_set_tuning', _lib.TUNE_DECODE_SCHEDULE, schedule)
         triangulate.lift_heatmaps(hm, center, scale, cams, conf_thre=0.5, return_idx=True, return_proj=True)
 poses = synth.random_poses(B, seed=1)
 obs, cams2 = synth.multiview_observations(poses, [rig], [0] * B, noise_px=2.0, outlier_frac=0.1, seed=2)
@@ -53,9 +53,9 @@ assert table.offset_only
 boxes = synth.crop_box(rig, poses[0])
 hm = synth.gaussian_heatmaps(rig, boxes, poses[0], 64, 256, 2.0, 0.02, seed=0)
 limb = synth.limb_lengths(poses[0], edges)
-for use_lut in (True, False):
+for use_lut, onchip in ((True, True), (True, False), (False, False)):
     pictorial.rpsm_batch(rig, hm[None], np.array([b['center'] for b in boxes]),
                          np.array([b['scale'] for b in boxes]), poses[0][:1], np.array([[limb[e] for e in edges]]),
-                         table, cfg, body, return_trace=True, use_lut=use_lut)
+                         table, cfg, body, return_trace=True, use_lut=use_lut, onchip=onchip)
 torch.cuda.synchronize()
 print('sanitize_small ok')

@@ -191,3 +191,38 @@ def test_pageable_host_pipeline_matches_the_plain_copy():
                 assert torch.equal(getattr(got, name), getattr(ref, name)), name
     finally:
         tri.STAGE_BYTES, tri.PAGEABLE_MIN_BYTES = old
+
+
+def test_full_size_launches_are_repeatable_and_schedule_independent():
+    """compute-sanitizer is closed on the pool, so race freedom of the hand-offs is checked the blunt way: the
+    BASELINE batch (4096 frames x 4 views x 17 joints x 64^2) lifted five times, with both decode map
+    schedules (static striding / strided share + claimed tail), must give identical bits every time -- a lost
+    update or a map decoded twice / not at all would show up as a differing or stale entry."""
+    from pose_unsupervised_b200 import runtime as rt
+    from pose_unsupervised_b200.multiviews.cameras import CameraTable, pack_camera
+    from pose_unsupervised_b200.multiviews.triangulate import lift_heatmaps
+    B, V, J = 4096, 4, 17
+    g = torch.Generator(device='cuda').manual_seed(7)
+    hm = torch.rand((B * V, J, 64, 64), generator=g, device='cuda', dtype=torch.float32)
+    rng = np.random.default_rng(7)
+    rigs = synth.camera_table(7, V, seed=0)
+    pack = np.array([pack_camera(c) for rig in rigs for c in rig])
+    subj = rng.integers(0, 7, B)
+    table = CameraTable.from_arrays(pack, (subj[:, None] * V + np.arange(V)[None]).reshape(-1))
+    center = rng.uniform(400, 600, (B * V, 2))
+    scale = np.repeat(rng.uniform(1.5, 3.0, (B * V, 1)), 2, axis=1)
+    try:
+        ref = None
+        for trial in range(5):
+            rt.set_decode_schedule(trial % 2 == 0)
+            xy_poison = None
+            res = lift_heatmaps(hm, center, scale, table, return_idx=True)
+            got = (res.idx.clone(), res.maxvals.clone(), res.xy.clone(), res.poses3d.clone(), res.reproj_err.clone())
+            if ref is None:
+                ref = got
+                assert torch.equal(ref[0].long(), hm.view(B * V, J, -1).argmax(dim=2))
+            else:
+                for a, b in zip(ref, got):
+                    assert torch.equal(a, b), trial
+    finally:
+        rt.set_decode_schedule(True)

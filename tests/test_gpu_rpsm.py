@@ -285,3 +285,39 @@ def test_rpsm_onchip_spills_vectors_for_deep_trees(pict):
     ref, rtrace = opict.rpsm(cams, hm, boxes, pose[0], limb, opict.level0_pairwise(2000, avg, 16, obody), cfg,
                              obody, return_trace=True)
     assert np.array_equal(t_on[0], rtrace) and np.array_equal(p_on[0], ref)
+
+
+def test_rpsm_full_batch_is_repeatable(pict):
+    """592 frames (4 per SM) three times: the on-chip kernel's stage hand-off, dynamic task hand-out and
+    cross-frame prefetch must give identical bins and poses on every launch."""
+    import torch
+    from pose_unsupervised_b200.multiviews.body import HumanBody
+    body, obody = HumanBody.h36m17(), h36m17()
+    edges = obody.edges()
+    cfg = rpsm_config()
+    base = 8
+    rng = np.random.default_rng(77)
+    avg = {e: float(np.mean([np.linalg.norm(p[e[0]] - p[e[1]]) for p in synth.random_poses(64, seed=99)]))
+           for e in edges}
+    table = pict.PairwiseTable.from_limb_lengths(avg, body, 2000, 16)
+    frames = []
+    for f in range(base):
+        pose = synth.random_poses(1, seed=500 + f)[0]
+        cams = synth.camera_ring(4, seed=600 + f)
+        boxes = synth.crop_box(cams, pose)
+        frames.append((pose, cams, boxes, synth.gaussian_heatmaps(cams, boxes, pose, 64, 256, 2.0, 0.02, seed=f),
+                       synth.limb_lengths(pose, edges)))
+    pick = rng.integers(0, base, 592)
+    hms = torch.from_numpy(np.array([frames[i][3] for i in range(base)])).cuda()[torch.from_numpy(pick).cuda()].contiguous()
+    cams = [c for i in pick for c in frames[i][1]]
+    centers = np.array([b['center'] for i in pick for b in frames[i][2]])
+    scales = np.array([b['scale'] for i in pick for b in frames[i][2]])
+    roots = np.array([frames[i][0][0] for i in pick]) + rng.normal(0, 40.0, (592, 3))
+    limbs = np.array([[frames[i][4][e] for e in edges] for i in pick])
+    first = None
+    for _ in range(3):
+        poses, trace = pict.rpsm_batch(cams, hms, centers, scales, roots, limbs, table, cfg, body, return_trace=True)
+        if first is None:
+            first = (poses.clone(), trace.clone())
+        else:
+            assert torch.equal(first[0], poses) and torch.equal(first[1], trace)
