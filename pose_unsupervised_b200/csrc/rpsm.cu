@@ -856,12 +856,19 @@ __device__ __forceinline__ unsigned oc_lds16(uint32_t a) {
   asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
   return v;
 }
+// Energy vectors of the on-chip kernel are stored x-FASTEST on the 16^3 grid: memory index m = (iy, iz, ix),
+// i.e. the logical bin index (iy, ix, iz) of pictorial.py:108-119 with its two low nibbles swapped.  The unary
+// samples arrive with lanes along grid x (fewer shared-memory bank conflicts when reading the staged maps, see
+// the sampling loop), so they are stored with unit stride, and the max-product walks along x just as well as
+// along z.  Everything visible outside the kernel (back pointers, traces, poses) uses logical indices.
+__device__ __forceinline__ int oc_swap(int j) { return (j & ~0xff) | ((j & 15) << 4) | ((j >> 4) & 15); }
+
 __device__ __forceinline__ uint4 oc_lds128(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
   return v;
 }
-// One candidate child from an edge's offset list.  `o2` = (ox + 8) | (k + 8) << 8, `d8` = (ox*16 + k)*8;
+// One candidate child from an edge's offset list.  `o2` = (ox + 8) | (k + 8) << 8, `d8` = (k*16 + ox)*8;
 // p2 = (ix + 8) | (iz + 8) << 8 of the lane's parent (0 for a lane that sits this task out).  Both child
 // coordinates are inside the 16-wide grid iff bits 4-5 of both byte sums read 01.  The child becomes the
 // running first maximum iff it is inside and STRICTLY larger -- children come in ascending index order.
@@ -896,8 +903,8 @@ __device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, u
                                                      const int* __restrict__ lcnt, const uint32_t* __restrict__ row0,
                                                      int r, int u, bool skip_ok) {
   const int lane = threadIdx.x & 31;
-  const int i = 32 * u + lane;                        // < 4096: every lane is a parent
-  const int iz = i & 15, ix = (i >> 4) & 15, iy = i >> 8;
+  const int i = 32 * u + lane;                        // memory index (iy, iz, ix) < 4096: every lane is a parent
+  const int ix = i & 15, iz = (i >> 4) & 15, iy = i >> 8;
   const double acc = oc_lds64(sD + (uint32_t)i * 8u);
   const bool skip = skip_ok && acc == 0.0;            // 0 * (finite max) = 0: argmax resolved only if ever needed
   double best = -INFINITY;
@@ -921,7 +928,7 @@ __device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, u
   }
   bool bad = false;
   if (!skip) {
-    const int found = fa != 0u ? (int)((fa - sS) >> 3) : -1;
+    const int found = fa != 0u ? oc_swap((int)((fa - sS) >> 3)) : -1;   // logical child index
     double val;
     int arg;
     oc_finish_max(row0, 16, 4096, iy, ix, iz, found, best, val, arg);
@@ -942,9 +949,11 @@ __device__ __forceinline__ bool oc_maxprod_unit_exact(const double* S, double* D
                                                       const uint16_t* __restrict__ dz, const uint32_t* __restrict__ row0,
                                                       int n0, int nb0, int r, int u, bool skip_ok) {
   const int lane = threadIdx.x & 31;
-  const int i = 32 * u + lane;
+  const int i = 32 * u + lane;                        // memory index
   if (i >= nb0) return false;
-  const int iz = i % n0, qi = i / n0, ix = qi % n0, iy = qi / n0;
+  const bool xfast = n0 == 16;
+  const int il = xfast ? oc_swap(i) : i;              // logical bin of this parent
+  const int iz = il % n0, qi = il / n0, ix = qi % n0, iy = qi / n0;
   const double acc = D[i];
   if (skip_ok && acc == 0.0) {
     D[i] = 0.0;
@@ -962,7 +971,7 @@ __device__ __forceinline__ bool oc_maxprod_unit_exact(const double* S, double* D
       const int base = row * n0;
       for (int jz = 0; jz < n0; ++jz)
         if ((dm >> abs(iz - jz)) & 1u) {
-          const double v = S[base + jz];
+          const double v = S[xfast ? oc_swap(base + jz) : base + jz];
           if (found < 0 || v > best) { best = v; found = base + jz; }
         }
     }
@@ -1100,7 +1109,7 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
         int o = rowoff[t];
         for (int k = -15; k <= 15; ++k)
           if ((m >> (k < 0 ? -k : k)) & 1u)
-            list[o++] = make_uint2((uint32_t)((ox + 8) | ((k + 8) << 8)), (uint32_t)((ox * 16 + k) * 8));
+            list[o++] = make_uint2((uint32_t)((ox + 8) | ((k + 8) << 8)), (uint32_t)((k * 16 + ox) * 8));
         if (local % w == w - 1 && ((o - os.loff[e][a]) & 1)) list[o] = make_uint2(0x3030u, 0u);   // padding
       }
     }
@@ -1143,12 +1152,11 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
     const double centre[3] = {p.root[3 * (size_t)f], p.root[3 * (size_t)f + 1], p.root[3 * (size_t)f + 2]};
 
     // ---- heatmap coordinates of every (bin, view), once per frame ---------------------------------
-    // Sampling order: slot s = tid + k*T holds bin slot_bin(s).  On the 16^3 grid the two low nibbles are
-    // swapped, so the 16 lanes of a half-warp walk along grid x instead of grid z: the vertical world axis
-    // projects to an image column, and with the 64-float pitch of a staged map the 16 taps of a column share
-    // ONE shared-memory bank; along x they spread over the banks.  The parked taps are stored by slot, so
-    // their loads stay coalesced.
-    auto slot_bin = [n0](int sl) { return n0 == 16 ? ((sl & ~0xff) | ((sl & 15) << 4) | ((sl >> 4) & 15)) : sl; };
+    // Slot s = tid + k*T is memory position s of the energy vectors = logical bin slot_bin(s).  On the 16^3 grid
+    // that is x-fastest, so the 16 lanes of a half-warp walk along grid x instead of grid z: the vertical world
+    // axis projects to an image column, and with the 64-float pitch of a staged map the 16 taps of a column share
+    // ONE shared-memory bank; along x they spread over the banks.  The parked taps are stored by slot.
+    auto slot_bin = [n0](int sl) { return n0 == 16 ? oc_swap(sl) : sl; };
     for (int sl = tid; sl < nb0; sl += T) {
       const int b = slot_bin(sl);
       double X[3];
@@ -1214,7 +1222,7 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
             const int sl = tid + k * T;
             if (sl < nb0) {
               if (!(fabs(u[k]) <= 1.79769313486231570e308)) os.nonfinite = 1;   // inf / NaN: no shortcuts
-              D[slot_bin(sl)] = u[k];
+              D[sl] = u[k];   // slot order IS the memory order of the energy vectors
             }
           }
         }
@@ -1252,9 +1260,10 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
         const double* er = vec(os.root_buf);
         double best = -INFINITY;
         int bidx = 0x7fffffff;
-        for (int b = tid; b < nb0; b += T) {
-          const double v = er[b];
-          if (bidx == 0x7fffffff || v > best) { best = v; bidx = b; }
+        for (int m = tid; m < nb0; m += T) {   // memory order; the first maximum is by LOGICAL index
+          const double v = er[m];
+          const int l = slot_bin(m);
+          if (bidx == 0x7fffffff || v > best || (v == best && l < bidx)) { best = v; bidx = l; }
         }
         warp_first_max(best, bidx);
         if (lane == 0) { s.red_val[warp] = best; s.red_idx[warp] = bidx; }
@@ -1271,7 +1280,7 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
             const int par = s.order[oi];
             for (int ce = os.child_start[par]; ce < os.child_start[par + 1]; ++ce) {
               const int e = os.child_edge[ce];
-              int b = bp[(size_t)e * nb0 + s.bin[par]];
+              int b = bp[(size_t)e * nb0 + (n0 == 16 ? oc_swap(s.bin[par]) : s.bin[par])];   // stored by memory index
               if (b == 0xffff) { redo = 1; b = 0; }
               s.bin[s.edge_c[e]] = b;
             }
