@@ -71,6 +71,19 @@ int pb200_crop_affine(const void* center, int center_dtype, const void* scale, i
                       const double* rot_sincos, double shift_x, double shift_y, int shift_dtype,
                       int n, int out_w, int out_h, int inv, double* out, void* stream);
 
+/* ---- debug-assert build ---------------------------------------------------------------
+ * A library compiled with -DPB200_DEBUG_CHECKS=1 (python -m pose_unsupervised_b200.build --debug ->
+ * libposeb200_debug.so) makes the kernels check the invariants their hand-offs rely on (map indices and
+ * counts of the decode schedule, candidate addresses / back pointers / task indices / stage contents of the
+ * on-chip RPSM, item indices of RANSAC).  pb200_debug_enabled() is 1 for such a build;
+ * pb200_debug_violations synchronises the device and copies the 16 violation counters (all zero in a
+ * release build), optionally resetting them.  Stands in for compute-sanitizer, which the GPU pool does
+ * not offer. */
+int pb200_debug_enabled(void);
+int pb200_debug_violations(int32_t* out16, int reset);
+/* debug build: one check that fails on purpose (counter 15 += 1); release build: PB200_ERR_UNSUPPORTED */
+int pb200_debug_selftest(void);
+
 /* ---- tuning (process-wide) --------------------------------------------------------
  * PB200_TUNE_DECODE_SCHEDULE: how the persistent decode kernel hands maps to its warps.
  *   PB200_DECODE_STATIC  warp w of block b takes maps b*8+w, +grid*8, ...
@@ -78,7 +91,7 @@ int pb200_crop_affine(const void* center, int center_dtype, const void* scale, i
  *                        in small batches from a counter: the end of the kernel evens out (1 % faster alone)
  *                        and a block that starts late because another kernel (an overlapped NCCL collective)
  *                        still holds its SM decodes fewer maps instead of finishing late.  The library keeps
- *                        a 32 KiB pool of claim counters per device for this (allocated on first use; a launch
+ *                        a 64 KiB pool of claim counters per device for this (allocated on first use; a launch
  *                        that finds none -- e.g. the first ever call happens inside a stream capture -- uses
  *                        the static form).  Results are identical.
  */

@@ -26,6 +26,9 @@ _PROTOS = {
     'pb200_last_error': (c_char_p, []),
     'pb200_device_check': (c_int, []),
     'pb200_sm_count': (c_int, []),
+    'pb200_debug_enabled': (c_int, []),
+    'pb200_debug_violations': (c_int, [c_void_p, c_int]),
+    'pb200_debug_selftest': (c_int, []),
     'pb200_set_tuning': (c_int, [c_int, c_int]),
     'pb200_crop_affine': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_double, c_double, c_int,
                                   c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -27,28 +27,36 @@ def find_nvcc():
     raise RuntimeError('nvcc not found; libposeb200.so cannot be built')
 
 
-def is_stale():
-    if not os.path.exists(LIB_PATH):
+def is_stale(path=None):
+    path = path or LIB_PATH
+    if not os.path.exists(path):
         return True
-    built = os.path.getmtime(LIB_PATH)
+    built = os.path.getmtime(path)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
     return any(os.path.getmtime(d) > built for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source into pose_unsupervised_b200/libposeb200.so."""
-    if not force and not is_stale():
-        return LIB_PATH
+DEBUG_LIB_PATH = os.path.join(PKG_DIR, 'libposeb200_debug.so')
+
+
+def build(force=False, verbose=False, debug=False):
+    """Compile every CUDA source into pose_unsupervised_b200/libposeb200.so (debug=True: the debug-assert
+    build libposeb200_debug.so, -DPB200_DEBUG_CHECKS=1, used by tests/test_gpu_debug_build.py)."""
+    out = DEBUG_LIB_PATH if debug else LIB_PATH
+    if not force and not is_stale(out):
+        return out
     extra = os.environ.get('PB200_NVCC_EXTRA', '').split()           # e.g. -DPB_STAGES=4 (tuning sweeps)
+    if debug:
+        extra = extra + ['-DPB200_DEBUG_CHECKS=1']
     cmd = [find_nvcc()] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + \
-        ['-o', LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+        ['-o', out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed (exit %d): %s' % (res.returncode, ' '.join(cmd)))
-    return LIB_PATH
+    return out
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, debug='--debug' in sys.argv))

@@ -40,7 +40,52 @@ int cached_sm_count() {
   return n;
 }
 
+#if PB200_DEBUG_CHECKS
+int debug_read_decode(int* acc16, int reset);
+int debug_read_geometry(int* acc16, int reset);
+int debug_read_rpsm(int* acc16, int reset);
+#endif
+
 }  // namespace pb200
+
+#if PB200_DEBUG_CHECKS
+namespace pb200 {
+__global__ void debug_selftest_kernel() { PB_DCHECK(threadIdx.x != 0, 15); }   // fails once, on purpose
+int debug_read_api(int* acc16, int reset);
+}  // namespace pb200
+PB_DEFINE_DEBUG_READER(api)
+#endif
+
+extern "C" int pb200_debug_enabled(void) { return PB200_DEBUG_CHECKS; }
+
+/* Debug build only: run one check that fails on purpose (counter 15 goes up by one), to show that the
+ * counters are alive.  Returns PB200_ERR_UNSUPPORTED in a release build. */
+extern "C" int pb200_debug_selftest(void) {
+#if PB200_DEBUG_CHECKS
+  pb200::debug_selftest_kernel<<<1, 32>>>();
+  PB_LAUNCH_CHECK("debug_selftest_kernel");
+  return PB200_OK;
+#else
+  pb200::set_error("not a debug build");
+  return PB200_ERR_UNSUPPORTED;
+#endif
+}
+
+extern "C" int pb200_debug_violations(int32_t* out16, int reset) {
+  PB_REQUIRE(out16 != nullptr, "out16 is null");
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+#if PB200_DEBUG_CHECKS
+  PB_CUDA(cudaDeviceSynchronize());
+  if (pb200::debug_read_decode(out16, reset) != 0 || pb200::debug_read_geometry(out16, reset) != 0 ||
+      pb200::debug_read_rpsm(out16, reset) != 0 || pb200::debug_read_api(out16, reset) != 0) {
+    pb200::set_error("reading the debug counters failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return PB200_ERR_CUDA;
+  }
+#else
+  (void)reset;
+#endif
+  return PB200_OK;
+}
 
 extern "C" int pb200_version(void) { return PB200_VERSION; }
 

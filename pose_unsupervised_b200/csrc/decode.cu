@@ -92,6 +92,10 @@ decode_tma_kernel(HmViews hv, int N, int J, int H, int W, const double* __restri
       },
       [&](int m, const DecodeOut& o) {
         if (lane == 0) {
+          PB_DCHECK(m >= 0 && m < total, kDbgDecodeMapRange);
+#if PB200_DEBUG_CHECKS
+          if (claim_ctr != nullptr) atomicAdd(claim_ctr + 2, 1);   // third word of the slot: maps decoded by this launch
+#endif
           reinterpret_cast<float2*>(out_xy)[m] = make_float2(o.x, o.y);
           out_maxval[m] = o.maxval;
           if (out_idx) out_idx[m] = o.idx;
@@ -104,12 +108,16 @@ decode_tma_kernel(HmViews hv, int N, int J, int H, int W, const double* __restri
     if (threadIdx.x == 0 && atomicAdd(claim_ctr + 1, 1) == (int)gridDim.x - 1) {
       claim_ctr[0] = 0;
       claim_ctr[1] = 0;
+#if PB200_DEBUG_CHECKS
+      __threadfence();
+      PB_DCHECK(atomicExch(claim_ctr + 2, 0) == total, kDbgDecodeMapCount);   // as many decodes as maps
+#endif
     }
   }
 }
 
 // ---- claim counters for the dynamic form -----------------------------------------------------------
-// A pool of (counter, blocks-done) pairs per device, zeroed once; every launch takes its own pair, so
+// A pool of (counter, blocks-done, [debug build: maps decoded], pad) slots per device, zeroed once; every launch takes its own pair, so
 // launches that overlap on different streams never share one: eager launches cycle through the first half
 // (a pair is back to zero long before it comes round again), launches recorded into a CUDA graph take a
 // pair of the second half for good (a graph cannot run concurrently with itself).  No pair left, or the
@@ -130,16 +138,16 @@ int* take_claim_pair(cudaStream_t stream) {
   if (pool->dev == nullptr) {
     if (capturing) return nullptr;                       // cannot zero the pool inside a capture
     int* d = nullptr;
-    if (cudaMalloc(&d, sizeof(int) * 2 * kClaimPairs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    if (cudaMemset(d, 0, sizeof(int) * 2 * kClaimPairs) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
-    pool->dev = d;                                       // 32 KiB per device, kept for the life of the process
+    if (cudaMalloc(&d, sizeof(int) * 4 * kClaimPairs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemset(d, 0, sizeof(int) * 4 * kClaimPairs) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
+    pool->dev = d;                                       // 64 KiB per device, kept for the life of the process
   }
   if (capturing) {
     const unsigned k = __sync_fetch_and_add(&pool->captured, 1u);
     if (k >= (unsigned)kClaimPairs / 2) return nullptr;
-    return pool->dev + 2 * (kClaimPairs / 2 + k);
+    return pool->dev + 4 * (kClaimPairs / 2 + k);
   }
-  return pool->dev + 2 * (__sync_fetch_and_add(&pool->eager, 1u) % (kClaimPairs / 2));
+  return pool->dev + 4 * (__sync_fetch_and_add(&pool->eager, 1u) % (kClaimPairs / 2));
 }
 }  // namespace
 
@@ -396,3 +404,5 @@ extern "C" int pb200_decode_flip(const float* const* hm_views_host, const float*
   PB_LAUNCH_CHECK("decode_flip_kernel");
   return PB200_OK;
 }
+
+PB_DEFINE_DEBUG_READER(decode)

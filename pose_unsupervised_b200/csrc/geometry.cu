@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(128) ransac_compact_kernel(GeoParams p, int ma
       if (!((mask >> a) & 1u)) continue;
       for (int b = a + 1; b < V; ++b) {
         if (!((mask >> b) & 1u)) continue;
+        PB_DCHECK(k < cap, kDbgRansacItem);
         items[k++] = PairItem{(uint8_t)lane, (uint8_t)a, (uint8_t)b, 0};   // combinations order
       }
     }
@@ -552,3 +553,5 @@ extern "C" int pb200_limb_break(const double* poses, const int32_t* edges, const
   PB_LAUNCH_CHECK("limb_break_kernel");
   return PB200_OK;
 }
+
+PB_DEFINE_DEBUG_READER(geometry)

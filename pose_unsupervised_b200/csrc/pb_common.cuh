@@ -56,6 +56,49 @@ struct PerDevice {
   }
 };
 
+// ---- debug-assert build (-DPB200_DEBUG_CHECKS=1): compute-sanitizer is not available on the GPU pool, so the
+// invariants the hand-offs rely on are checked by the kernels themselves in a second build of the library.  A
+// failed check bumps one of 16 counters (pb200_debug_violations reads them); the release build compiles the
+// checks away.  tests/test_gpu_debug_build.py runs the hot path through that build.
+#ifndef PB200_DEBUG_CHECKS
+#define PB200_DEBUG_CHECKS 0
+#endif
+enum {
+  kDbgDecodeMapRange = 0,     // a decode warp was handed a map index outside [0, total)
+  kDbgDecodeMapCount = 1,     // maps decoded in one launch != N*J
+  kDbgRpsmCandAddr = 2,       // an in-grid candidate address outside the source vector
+  kDbgRpsmArg = 3,            // a back pointer outside [0, nbins)
+  kDbgRpsmUnit = 4,           // a warp task index outside [0, nunits)
+  kDbgRpsmStage = 5,          // the stage was read while it held another (frame, joint, group)
+  kDbgRpsmList = 6,           // the offset lists overflow their shared-memory area
+  kDbgRansacItem = 7,         // a (joint, pair) item index outside the warp's list
+};
+#if PB200_DEBUG_CHECKS
+// one copy per translation unit (the library is built without relocatable device code); every .cu that uses
+// PB_DCHECK defines a reader with PB_DEFINE_DEBUG_READER and api.cu adds the copies up
+static __device__ int g_debug_violations[16];
+#define PB_DCHECK(cond, code)                                       \
+  do {                                                              \
+    if (!(cond)) atomicAdd(&pb200::g_debug_violations[code], 1);    \
+  } while (0)
+#define PB_DEFINE_DEBUG_READER(name)                                                                   \
+  namespace pb200 {                                                                                    \
+  int debug_read_##name(int* acc16, int reset) {                                                       \
+    int local[16];                                                                                     \
+    if (cudaMemcpyFromSymbol(local, g_debug_violations, sizeof(local)) != cudaSuccess) return -1;      \
+    for (int i = 0; i < 16; ++i) acc16[i] += local[i];                                                 \
+    if (reset) {                                                                                       \
+      int zeros[16] = {0};                                                                             \
+      if (cudaMemcpyToSymbol(g_debug_violations, zeros, sizeof(zeros)) != cudaSuccess) return -1;      \
+    }                                                                                                  \
+    return 0;                                                                                          \
+  }                                                                                                    \
+  }
+#else
+#define PB_DCHECK(cond, code) do { } while (0)
+#define PB_DEFINE_DEBUG_READER(name)
+#endif
+
 struct HmViews {
   const float* ptr[PB200_MAX_VIEWS];
   int n;  // 1 (single [N,J,H,W] tensor) or V (per-view tensors [N/V,J,H,W])

@@ -921,6 +921,14 @@ __device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, u
 #pragma unroll 2
       for (int t = 0; t < n; t += 2, la += 16u) {
         const uint4 e = oc_lds128(la);                // two entries, the same for every lane
+#if PB200_DEBUG_CHECKS
+        for (int h = 0; h < 2; ++h) {                 // an in-grid candidate must lie inside the source vector
+          const uint32_t o2 = h ? e.z : e.x, d8 = h ? e.w : e.y;
+          const bool inside = (((o2 + p2) & 0x3030u) ^ 0x1010u) == 0u;
+          const uint32_t a = base + d8;
+          PB_DCHECK(!inside || (a >= sS && a < sS + 4096u * 8u), kDbgRpsmCandAddr);
+        }
+#endif
         oc_cand(e.x, e.y, p2, base, best, fa);
         oc_cand(e.z, e.w, p2, base, best, fa);
       }
@@ -928,10 +936,12 @@ __device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, u
   }
   bool bad = false;
   if (!skip) {
+    PB_DCHECK(fa == 0u || (fa >= sS && fa < sS + 4096u * 8u && ((fa - sS) & 7u) == 0u), kDbgRpsmCandAddr);
     const int found = fa != 0u ? oc_swap((int)((fa - sS) >> 3)) : -1;   // logical child index
     double val;
     int arg;
     oc_finish_max(row0, 16, 4096, iy, ix, iz, found, best, val, arg);
+    PB_DCHECK(arg >= 0 && arg < 4096, kDbgRpsmArg);
     const double out = acc * val;
     bad = !(fabs(out) <= 1.79769313486231570e308);
     oc_sts64(sD + (uint32_t)i * 8u, out);
@@ -1096,6 +1106,7 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
         }
       }
       os.use_flat = (n0 == 16 && off <= L.list_cap) ? 1 : 0;
+      PB_DCHECK(off <= L.list_cap || os.use_flat == 0, kDbgRpsmList);
     }
     __syncthreads();
     if (os.use_flat) {
@@ -1138,6 +1149,7 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
       __syncthreads();
     }
     oc_mbar_wait(mbar, (os.stage_seq - 1) & 1u);
+    PB_DCHECK(os.stage_tag == tag, kDbgRpsmStage);   // what is about to be sampled is what was copied
   };
 
   for (int f = blockIdx.x; f < p.B; f += gridDim.x) {
@@ -1242,6 +1254,7 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
             t = __shfl_sync(0xffffffffu, t, 0);
             if (t >= nunits) break;
             const int u = os.unit_order[t];
+            PB_DCHECK(u >= 0 && u < nunits, kDbgRpsmUnit);
             if (flat)   // everything on chip, every lane walks the edge's offset list
               bad |= oc_maxprod_unit_flat(vec_s + (uint32_t)((size_t)op.src * L.vec_stride * 8),
                                           vec_s + (uint32_t)((size_t)op.dst * L.vec_stride * 8), bp + (size_t)e * nb0,
@@ -1566,3 +1579,5 @@ extern "C" int pb200_pairwise_lut_check(const uint32_t* pair_bits, int E, int nb
   PB_LAUNCH_CHECK("pairwise_lut_check_kernel");
   return PB200_OK;
 }
+
+PB_DEFINE_DEBUG_READER(rpsm)
