@@ -125,3 +125,32 @@ def test_pairwise_bit_packing_layout():
         pack_pairwise_bits(np.full((4, 4), 2))
     with pytest.raises(ValueError):
         pack_pairwise_bits(np.zeros((4, 5)))
+
+
+def test_tuning_and_debug_entry_points_need_no_device(lib):
+    """pb200_set_tuning validates key and value on the host; the release build reports that it is not a debug
+    build, hands back zeroed counters and refuses the self-test."""
+    import ctypes
+    assert lib.pb200_set_tuning(_lib.TUNE_DECODE_SCHEDULE, _lib.DECODE_STATIC) == 0
+    assert lib.pb200_set_tuning(_lib.TUNE_DECODE_SCHEDULE, _lib.DECODE_DYNAMIC) == 0
+    assert lib.pb200_set_tuning(_lib.TUNE_DECODE_SCHEDULE, 7) != 0 and b'schedule' in lib.pb200_last_error()
+    assert lib.pb200_set_tuning(99, 0) != 0 and b'unknown tuning key' in lib.pb200_last_error()
+    assert lib.pb200_debug_enabled() == 0
+    counters = (ctypes.c_int32 * 16)(*([5] * 16))
+    assert lib.pb200_debug_violations(counters, 0) == 0 and not any(counters)
+    assert lib.pb200_debug_selftest() != 0
+    assert lib.pb200_debug_violations(None, 0) != 0
+
+
+def test_debug_build_exports_the_same_abi():
+    """libposeb200_debug.so (built by __graft_entry__.build()) exports every symbol of the header too."""
+    import ctypes
+    import os
+    path = os.path.join(os.path.dirname(_lib.LIB_PATH), 'libposeb200_debug.so')
+    if not os.path.exists(path):
+        pytest.skip('debug build not present')
+    dbg = ctypes.CDLL(path)
+    for name in _lib.EXPORTED_SYMBOLS:
+        assert hasattr(dbg, name), name
+    dbg.pb200_debug_enabled.restype = ctypes.c_int
+    assert dbg.pb200_debug_enabled() == 1
