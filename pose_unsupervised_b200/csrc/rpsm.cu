@@ -564,7 +564,7 @@ struct OcLayout {   // filled by the host (rpsm_onchip_layout)
   double* coords_ws;            // [blocks][V][nb0][2]  bilinear fractions
   int32_t* tap_ws;              // [blocks][V][nb0]     top-left tap of the sample
   double* spill_ws;             // [blocks][nspill][vec_stride]
-  uint16_t* bp_ws;              // [blocks][E][nb0]
+  double* sfin_ws;              // [blocks][E][vec_stride]  every child's final energy vector (back-tracking)
 };
 
 struct OcShared {
@@ -573,19 +573,25 @@ struct OcShared {
   int nops, nsamp, root_buf, prog_err;
   int reach[kRpsmMaxJ];
   int doff[kRpsmMaxJ + 1];      // offset of edge e in the |dz| table
-  int loff[kRpsmMaxJ][8];       // offset / (even) length of the offset-list slice of (edge, |oy|)
-  int lcnt[kRpsmMaxJ][8];
+  uint16_t loff[kRpsmMaxJ][8][3];   // offset / (even) length of the three offset sub-lists of (edge, |oy|):
+  uint16_t lcnt[kRpsmMaxJ][8][3];   // children of parent A only, of both parents of a lane, of parent B only
   int use_flat;                 // 1: the offset lists of all edges fit in shared memory and n0 = 16
   int child_start[kRpsmMaxJ + 1];
   uint8_t child_edge[kRpsmMaxJ];
   uint8_t samp_joint[kRpsmMaxJ];
   uint8_t unit_order[kOcMaxUnits];
+  uint8_t pair_order[64];       // the 64 warp tasks of the fast form (64 parents each), interior first
   uint8_t pmask[kRpsmMaxJ * 8]; // refinement: allowed child bins (bit j) per (edge, parent bin)
+  uint8_t bt_edge[kRpsmMaxJ];   // edges sorted by the tree depth of their child joint (root's children: 1) ...
+  uint8_t bt_start[kRpsmMaxJ + 2];   // ... and where depth d starts in that list: the back-tracking order
+  int max_depth;
+  double bt_val[kOcThreads / 32], bt_fval[kOcThreads / 32];   // back-tracking: per-warp partial results
+  int bt_idx[kOcThreads / 32], bt_fidx[kOcThreads / 32];
   unsigned long long mbar;
   long long stage_tag;          // (frame, sample slot, group) of the bulk copy issued last; -1 = none
   unsigned stage_seq;           // bulk-copy groups issued so far (mbarrier phase = stage_seq - 1)
   int unit_next;                // next warp task of the running max-product
-  int nonfinite, redo, skip_ok;
+  int nonfinite;
 };
 
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
@@ -718,6 +724,29 @@ __device__ void oc_build_program(OcShared& os, int J, int E, int root_idx, int n
       if (s.edge_p[e] == j) os.child_edge[ce++] = (uint8_t)e;
   }
   os.child_start[J] = ce;
+  int md = 0;
+  uint8_t depth[kRpsmMaxJ];
+  for (int e = 0; e < E; ++e) {
+    int d = 1, j = s.edge_p[e];
+    for (int guard = 0; j != root_idx && guard < E; ++guard) {
+      int up = -1;
+      for (int q = 0; q < E; ++q)
+        if (s.edge_c[q] == j) up = s.edge_p[q];
+      if (up < 0) break;
+      j = up;
+      ++d;
+    }
+    depth[e] = (uint8_t)d;
+    md = d > md ? d : md;
+  }
+  os.max_depth = md;
+  int pos = 0;
+  for (int d = 1; d <= md; ++d) {
+    os.bt_start[d] = (uint8_t)pos;
+    for (int e = 0; e < E; ++e)
+      if (depth[e] == d) os.bt_edge[pos++] = (uint8_t)e;
+  }
+  os.bt_start[md + 1] = (uint8_t)pos;
 }
 
 // ---- refinement levels for 2^3 grids (the reference's RECUR_NBINS = 2), block-wide ------------------
@@ -870,94 +899,150 @@ __device__ __forceinline__ uint4 oc_lds128(uint32_t a) {
 }
 // One candidate child from an edge's offset list.  `o2` = (ox + 8) | (k + 8) << 8, `d8` = (k*16 + ox)*8;
 // p2 = (ix + 8) | (iz + 8) << 8 of the lane's parent (0 for a lane that sits this task out).  Both child
-// coordinates are inside the 16-wide grid iff bits 4-5 of both byte sums read 01.  The child becomes the
-// running first maximum iff it is inside and STRICTLY larger -- children come in ascending index order.
-__device__ __forceinline__ void oc_cand(uint32_t o2, uint32_t d8, uint32_t p2, uint32_t base, double& best,
-                                        uint32_t& fa) {
+// coordinates are inside the 16-wide grid iff bits 4-5 of both byte sums read 01.  The forward pass only needs
+// the VALUE of the maximum: which child attains it is resolved during back-tracking, for the one parent bin per
+// edge that lies on the chosen pose (oc_backtrack).  Lanes whose child is outside do not load at all (a
+// redirected load to a cell holding -inf costs a bank conflict per half-warp: measured 133 k frames/s vs 168 k).
+// `v` is the caller's scratch for the loaded energy: a lane outside keeps whatever it held (the compare is masked),
+// and naming it -- four of them, used in rotation -- keeps the compiler from inventing a loop-carried register
+// per candidate for that "old value", which is what spilled.
+__device__ __forceinline__ void oc_cand(uint32_t o2, uint32_t d8, uint32_t p2, uint32_t base, double& best, double& v) {
   asm volatile(
       "{\n\t"
       ".reg .pred p, q, f;\n\t"
       ".reg .b32 s, d;\n\t"
-      ".reg .f64 v;\n\t"
       "add.u32 s, %2, %4;\n\t"
       "setp.ne.u32 f, 0, 0;\n\t"
       "lop3.or.b32 s|q, s, 0x3030, 0x1010, 0x6A, f;\n\t"   /* q = ((s & 0x3030) ^ 0x1010) != 0: OUTSIDE */
-      "not.pred q, q;\n\t"
       "add.u32 d, %5, %3;\n\t"
-      "@q ld.shared.f64 v, [d];\n\t"                 /* v is undefined when !q; the compare below is masked by q */
-      "setp.gt.and.f64 p, v, %0, q;\n\t"
-      "selp.f64 %0, v, %0, p;\n\t"
-      "selp.b32 %1, d, %1, p;\n\t"
-      "}" : "+d"(best), "+r"(fa) : "r"(o2), "r"(d8), "r"(p2), "r"(base) : "memory");
+      "@!q ld.shared.f64 %1, [d];\n\t"
+      "setp.gt.and.f64 p, %1, %0, !q;\n\t"
+      "@p mov.f64 %0, %1;\n\t"
+      "}" : "+d"(best), "+d"(v) : "r"(o2), "r"(d8), "r"(p2), "r"(base) : "memory");
 }
 
-// One warp task of the max-product: the 32 consecutive parent bins [32u, 32u+32) of edge e (n0 = 16).
-//   D[i] <- D[i] * max_j ( P[i,j] ? S[j] : 0 ),  bp[i] <- first argmax           (pictorial.py:50-56)
-// FAST FORM (source and destination in shared memory, finite frame): the allowed children of the edge
-// are a LIST of offsets, sorted by ascending child index and cut into slices by |oy|; it is the same for
-// every parent, so all lanes walk it in lock step -- no divergence, no per-row bookkeeping -- and a lane
-// only masks the children that fall outside the grid.  sList: shared address of the block's lists (8-byte
-// entries), loff / lcnt: offset and (even) length of the edge's slices.
-__device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, uint16_t* __restrict__ bp_e,
-                                                     uint32_t sList, const int* __restrict__ loff,
-                                                     const int* __restrict__ lcnt, const uint32_t* __restrict__ row0,
-                                                     int r, int u, bool skip_ok) {
-  const int lane = threadIdx.x & 31;
-  const int i = 32 * u + lane;                        // memory index (iy, iz, ix) < 4096: every lane is a parent
-  const int ix = i & 15, iz = (i >> 4) & 15, iy = i >> 8;
-  const double acc = oc_lds64(sD + (uint32_t)i * 8u);
-  const bool skip = skip_ok && acc == 0.0;            // 0 * (finite max) = 0: argmax resolved only if ever needed
-  double best = -INFINITY;
-  uint32_t fa = 0u;                                   // shared address of the running first maximum
-  if (__any_sync(0xffffffffu, !skip)) {
-    const uint32_t p2 = skip ? 0u : (uint32_t)((ix + 8) | ((iz + 8) << 8));
-    const int iyu = u >> 3;                           // all 32 parents of a task share iy
-    for (int oy = -r; oy <= r; ++oy) {
-      if ((unsigned)(iyu + oy) >= 16u) continue;
-      const int aoy = oy < 0 ? -oy : oy;
-      const uint32_t base = sS + (uint32_t)((i + oy * 256) * 8);
-      uint32_t la = sList + (uint32_t)loff[aoy] * 8u;
-      const int n = lcnt[aoy];
-#pragma unroll 2
-      for (int t = 0; t < n; t += 2, la += 16u) {
-        const uint4 e = oc_lds128(la);                // two entries, the same for every lane
-#if PB200_DEBUG_CHECKS
-        for (int h = 0; h < 2; ++h) {                 // an in-grid candidate must lie inside the source vector
-          const uint32_t o2 = h ? e.z : e.x, d8 = h ? e.w : e.y;
-          const bool inside = (((o2 + p2) & 0x3030u) ^ 0x1010u) == 0u;
-          const uint32_t a = base + d8;
-          PB_DCHECK(!inside || (a >= sS && a < sS + 4096u * 8u), kDbgRpsmCandAddr);
-        }
+// The factor a parent's energy is multiplied with, from the maximum over its allowed in-grid children
+// (`best`, -inf when it has none): max_j ( P[i,j] ? S[j] : 0 ) of pictorial.py:50-56 with the zeros of the
+// disallowed children taken into account.
+__device__ __forceinline__ double oc_factor(const uint32_t* __restrict__ row0, int n0, int nb0, int iy, int ix, int iz,
+                                            bool any, double best) {
+  if (any && best > 0.0) return best;
+  double val;
+  int arg;
+  oc_finish_max(row0, n0, nb0, iy, ix, iz, any ? 0 : -1, best, val, arg);   // (val does not depend on `found`'s value)
+  return val;
+}
+
+// The same candidate offered to the two parents of a lane (it is z-neighbour k' of one and k'-1 of the other).
+__device__ __forceinline__ void oc_cand2(uint32_t o2, uint32_t d8, uint32_t p2, uint32_t base, double& bestA,
+                                         double& bestB, double& v) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pa, pb, q, f;\n\t"
+      ".reg .b32 s, d;\n\t"
+      "add.u32 s, %3, %5;\n\t"
+      "setp.ne.u32 f, 0, 0;\n\t"
+      "lop3.or.b32 s|q, s, 0x3030, 0x1010, 0x6A, f;\n\t"
+      "add.u32 d, %6, %4;\n\t"
+      "@!q ld.shared.f64 %2, [d];\n\t"
+      "setp.gt.and.f64 pa, %2, %0, !q;\n\t"
+      "setp.gt.and.f64 pb, %2, %1, !q;\n\t"
+      "@pa mov.f64 %0, %2;\n\t"
+      "@pb mov.f64 %1, %2;\n\t"
+      "}" : "+d"(bestA), "+d"(bestB), "+d"(v) : "r"(o2), "r"(d8), "r"(p2), "r"(base) : "memory");
+}
+__device__ __forceinline__ void oc_cand_check(uint32_t o2, uint32_t d8, uint32_t p2, uint32_t base, uint32_t sS) {
+#if PB200_DEBUG_CHECKS   // an in-grid candidate must lie inside the source vector
+  const bool inside = (((o2 + p2) & 0x3030u) ^ 0x1010u) == 0u;
+  const uint32_t a = base + d8;
+  PB_DCHECK(!inside || (a >= sS && a < sS + 4096u * 8u), kDbgRpsmCandAddr);
 #endif
-        oc_cand(e.x, e.y, p2, base, best, fa);
-        oc_cand(e.z, e.w, p2, base, best, fa);
+}
+
+// One warp task of the max-product, FAST FORM (n0 = 16, source and destination in shared memory, finite frame):
+//   D[i] <- D[i] * max_j ( P[i,j] ? S[j] : 0 )                                  (pictorial.py:50-56)
+// for the 64 parents (iy, z in [4q, 4q+4), all ix) of task u = 4 iy + q.  A lane owns TWO parents, A = (iy, z0, ix)
+// and B = (iy, z0+1, ix) with z0 = 4q + 2 (lane / 16): a child at z-offset k' from z0 is neighbour k' of A and
+// k'-1 of B, and the allowed z-offsets of a row (oy, ox) come in runs, so most children serve both -- one
+// shared-memory read, two comparisons.  The allowed children of the edge are LISTS of offsets (o2, d8 as in
+// oc_cand, k' in place of k), cut into slices by |oy| and, within a slice, into the children of A only, of
+// both, and of B only; they are the same for every lane, so all lanes walk them in lock step and a lane only
+// masks the children that fall outside the grid.  The order of the walk is free: only the VALUE of the maximum
+// is needed here (oc_cand).  sList: shared address of the block's lists, loff / lcnt: the edge's sub-lists.
+__device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, uint32_t sList,
+                                                     const uint16_t (*__restrict__ loff)[3],
+                                                     const uint16_t (*__restrict__ lcnt)[3],
+                                                     const uint32_t* __restrict__ row0, int r, int u) {
+  const int lane = threadIdx.x & 31;
+  const int ix = lane & 15, z0 = 4 * (u & 3) + 2 * (lane >> 4), iy = u >> 2;
+  const int iA = iy * 256 + z0 * 16 + ix;             // memory index (iy, iz, ix) of parent A; B = iA + 16
+  const double accA = oc_lds64(sD + (uint32_t)iA * 8u), accB = oc_lds64(sD + (uint32_t)(iA + 16) * 8u);
+  const bool skipA = accA == 0.0, skipB = accB == 0.0;   // 0 * (finite max) = 0
+  double bestA = -INFINITY, bestB = -INFINITY;
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+  if (__any_sync(0xffffffffu, !(skipA && skipB))) {
+    const uint32_t p2 = (skipA && skipB) ? 0u : (uint32_t)((ix + 8) | ((z0 + 8) << 8));
+    for (int oy = -r; oy <= r; ++oy) {
+      if ((unsigned)(iy + oy) >= 16u) continue;       // (all parents of a task share iy)
+      const int aoy = oy < 0 ? -oy : oy;
+      const uint32_t base = sS + (uint32_t)((iA + oy * 256) * 8);
+      // each sub-list four entries per trip (its length is even), the loaded energies in v0..v3
+#define OC_WALK(SUB, CAND)                                                                      \
+      {                                                                                           \
+        uint32_t la = sList + (uint32_t)loff[aoy][SUB] * 8u;                                      \
+        const int n = lcnt[aoy][SUB];                                                             \
+        int t = 0;                                                                                \
+        for (; t + 4 <= n; t += 4, la += 32u) {                                                   \
+          const uint4 e = oc_lds128(la), g = oc_lds128(la + 16u); /* the same for every lane */  \
+          oc_cand_check(e.x, e.y, p2, base, sS);                                                  \
+          oc_cand_check(e.z, e.w, p2, base, sS);                                                  \
+          oc_cand_check(g.x, g.y, p2, base, sS);                                                  \
+          oc_cand_check(g.z, g.w, p2, base, sS);                                                  \
+          CAND(e.x, e.y, v0);                                                                     \
+          CAND(e.z, e.w, v1);                                                                     \
+          CAND(g.x, g.y, v2);                                                                     \
+          CAND(g.z, g.w, v3);                                                                     \
+        }                                                                                         \
+        if (t < n) {                                                                              \
+          const uint4 e = oc_lds128(la);                                                          \
+          oc_cand_check(e.x, e.y, p2, base, sS);                                                  \
+          oc_cand_check(e.z, e.w, p2, base, sS);                                                  \
+          CAND(e.x, e.y, v0);                                                                     \
+          CAND(e.z, e.w, v1);                                                                     \
+        }                                                                                         \
       }
+#define OC_CAND_A(o2, d8, v) oc_cand(o2, d8, p2, base, bestA, v)
+#define OC_CAND_AB(o2, d8, v) oc_cand2(o2, d8, p2, base, bestA, bestB, v)
+#define OC_CAND_B(o2, d8, v) oc_cand(o2, d8, p2, base, bestB, v)
+      OC_WALK(0, OC_CAND_A)
+      OC_WALK(1, OC_CAND_AB)
+      OC_WALK(2, OC_CAND_B)
+#undef OC_CAND_A
+#undef OC_CAND_AB
+#undef OC_CAND_B
+#undef OC_WALK
     }
   }
+  // (a finite frame: -inf can only be the initial value, i.e. no allowed child inside the grid)
   bool bad = false;
-  if (!skip) {
-    PB_DCHECK(fa == 0u || (fa >= sS && fa < sS + 4096u * 8u && ((fa - sS) & 7u) == 0u), kDbgRpsmCandAddr);
-    const int found = fa != 0u ? oc_swap((int)((fa - sS) >> 3)) : -1;   // logical child index
-    double val;
-    int arg;
-    oc_finish_max(row0, 16, 4096, iy, ix, iz, found, best, val, arg);
-    PB_DCHECK(arg >= 0 && arg < 4096, kDbgRpsmArg);
-    const double out = acc * val;
-    bad = !(fabs(out) <= 1.79769313486231570e308);
-    oc_sts64(sD + (uint32_t)i * 8u, out);
-    bp_e[i] = (uint16_t)arg;
-  } else {
-    oc_sts64(sD + (uint32_t)i * 8u, 0.0);
-    bp_e[i] = (uint16_t)0xffff;
+  {
+    const double out = skipA ? 0.0 : accA * oc_factor(row0, 16, 4096, iy, ix, z0, bestA != -INFINITY, bestA);
+    bad |= !(fabs(out) <= 1.79769313486231570e308);
+    oc_sts64(sD + (uint32_t)iA * 8u, out);
+  }
+  {
+    const double out = skipB ? 0.0 : accB * oc_factor(row0, 16, 4096, iy, ix, z0 + 1, bestB != -INFINITY, bestB);
+    bad |= !(fabs(out) <= 1.79769313486231570e308);
+    oc_sts64(sD + (uint32_t)(iA + 16) * 8u, out);
   }
   return bad;
 }
 
 // EXACT PER-LANE FORM (vectors spilled to scratch, |dz| sets with gaps, or non-finite energies): every lane
 // enumerates its own allowed children with the reference's first-candidate rule.
-__device__ __forceinline__ bool oc_maxprod_unit_exact(const double* S, double* D, uint16_t* __restrict__ bp_e,
-                                                      const uint16_t* __restrict__ dz, const uint32_t* __restrict__ row0,
-                                                      int n0, int nb0, int r, int u, bool skip_ok) {
+__device__ __forceinline__ bool oc_maxprod_unit_exact(const double* S, double* D, const uint16_t* __restrict__ dz,
+                                                      const uint32_t* __restrict__ row0, int n0, int nb0, int r,
+                                                      int u, bool skip_ok) {
   const int lane = threadIdx.x & 31;
   const int i = 32 * u + lane;                        // memory index
   if (i >= nb0) return false;
@@ -967,7 +1052,6 @@ __device__ __forceinline__ bool oc_maxprod_unit_exact(const double* S, double* D
   const double acc = D[i];
   if (skip_ok && acc == 0.0) {
     D[i] = 0.0;
-    bp_e[i] = (uint16_t)0xffff;
     return false;
   }
   const int w = 2 * r + 1;
@@ -990,8 +1074,70 @@ __device__ __forceinline__ bool oc_maxprod_unit_exact(const double* S, double* D
   oc_finish_max(row0, n0, nb0, iy, ix, iz, found, best, val, arg);
   const double out = acc * val;
   D[i] = out;
-  bp_e[i] = (uint16_t)arg;
   return !(fabs(out) <= 1.79769313486231570e308);
+}
+
+// Back-tracking of one edge: the first argmax over the children of parent bin `par` (logical index), from the
+// child's final energy vector Sg (scratch, memory order).  Same rule as the sequential enumeration above -- the
+// first allowed child is taken unconditionally, a later one only if STRICTLY larger -- evaluated in parallel:
+// a partial result is (best, found) = first maximum among the non-NaN children seen, and (first_v, first) = the
+// lowest child seen; partial results merge associatively, and a NaN in the very first position wins at the end.
+struct OcPick {
+  double best, first_v;
+  int found, first;
+};
+__device__ __forceinline__ void oc_pick_merge(OcPick& a, double ob, int of, double ofv, int ofi) {
+  if (of >= 0 && (a.found < 0 || ob > a.best || (ob == a.best && of < a.found))) { a.best = ob; a.found = of; }
+  if (ofi < a.first) { a.first = ofi; a.first_v = ofv; }
+}
+template <int WIDTH>
+__device__ __forceinline__ void oc_pick_reduce(OcPick& a) {
+#pragma unroll
+  for (int o = WIDTH / 2; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, a.best, o), ofv = __shfl_xor_sync(0xffffffffu, a.first_v, o);
+    const int of = __shfl_xor_sync(0xffffffffu, a.found, o), ofi = __shfl_xor_sync(0xffffffffu, a.first, o);
+    oc_pick_merge(a, ob, of, ofv, ofi);
+  }
+}
+// One thread's share: row t = (jy, jx) of the (2r+1)^2 neighbourhood of `par`, all jz; 8 independent loads at a time.
+__device__ __forceinline__ OcPick oc_pick_row(const double* __restrict__ Sg, const uint16_t* __restrict__ dz, int n0,
+                                              int r, int par, int t) {
+  OcPick a;
+  a.best = -INFINITY; a.first_v = 0.0; a.found = -1; a.first = 0x7fffffff;
+  const bool xfast = n0 == 16;
+  const int iz = par % n0, qi = par / n0, ix = qi % n0, iy = qi / n0;
+  const int w = 2 * r + 1;
+  if (t >= w * w) return a;
+  const int ty = t / w, jy = iy - r + ty, jx = ix - r + (t - ty * w);
+  if ((unsigned)jy >= (unsigned)n0 || (unsigned)jx >= (unsigned)n0) return a;
+  const unsigned dm = dz[abs(iy - jy) * w + (jx - ix) + r];
+  const int base = (jy * n0 + jx) * n0;
+  for (int z0 = 0; z0 < n0; z0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int jz = z0 + q;
+      const bool ok = jz < n0 && ((dm >> abs(iz - jz)) & 1u);
+      v[q] = ok ? __ldcg(Sg + (xfast ? oc_swap(base + jz) : base + jz)) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int jz = z0 + q;
+      if (jz < n0 && ((dm >> abs(iz - jz)) & 1u)) {   // ascending child index
+        if (a.first == 0x7fffffff) { a.first = base + jz; a.first_v = v[q]; }
+        if ((a.found < 0 && v[q] == v[q]) || v[q] > a.best) { a.best = v[q]; a.found = base + jz; }
+      }
+    }
+  }
+  return a;
+}
+__device__ __forceinline__ int oc_pick_finish(OcPick a, const uint32_t* __restrict__ row0, int n0, int nb0, int par) {
+  if (a.first != 0x7fffffff && a.first_v != a.first_v) { a.best = a.first_v; a.found = a.first; }   // a NaN in front stays
+  const int iz = par % n0, qi = par / n0, ix = qi % n0, iy = qi / n0;
+  double val;
+  int arg;
+  oc_finish_max(row0, n0, nb0, iy, ix, iz, a.found, a.best, val, arg);
+  return arg;
 }
 
 __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmParams p, const OcLayout L) {
@@ -1015,7 +1161,7 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
   double* coords = L.coords_ws + (size_t)blockIdx.x * V * nb0 * 2;   // (fx, fy) of every (view, bin)
   int32_t* tappos = L.tap_ws + (size_t)blockIdx.x * V * nb0;         // top-left tap, or outside / NaN
   double* spill = L.spill_ws + (size_t)blockIdx.x * L.nspill * L.vec_stride;
-  uint16_t* bp = L.bp_ws + (size_t)blockIdx.x * E * nb0;
+  double* sfin = L.sfin_ws + (size_t)blockIdx.x * E * L.vec_stride;
   const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&os.mbar);
   const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
   const uint32_t vec_s = (uint32_t)__cvta_generic_to_shared(vec_sm);
@@ -1086,43 +1232,71 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
   }
   __syncthreads();
   // ---- the edges' child-offset lists (fast form of the max-product, n0 = 16) ------------------------
-  // Row (e, |oy|, ox) contributes its allowed k = -15..15 in ascending order; rows are laid out slice by
-  // slice (e, |oy|), each padded to an even number of entries with one that is outside for every parent.
+  // Row (e, |oy|, ox) has the allowed z-offsets K (from its |dz| set).  For the parent pair (z0, z0+1) of a lane
+  // the children at z0 + k' are: of A only, k' in K \ (K+1); of both, K & (K+1); of B only, (K+1) \ K.  Each
+  // slice (e, |oy|) stores the three sub-lists, rows in order, each padded to an even number of entries with
+  // one that is outside for every parent.  Bit (k' + 15) of a 32-bit word stands for k' = -15..16.
   {
     int32_t* rowoff = reinterpret_cast<int32_t*>(vec_sm);   // scratch: the energy vectors are not in use yet
-    if (tid == 0) {
+    const int rows = os.doff[E];
+    auto sub_bits = [](unsigned m, int sub) -> uint32_t {
+      uint32_t K = 0u;
+      for (int d = 0; d < 16; ++d)
+        if ((m >> d) & 1u) K |= (1u << (15 + d)) | (1u << (15 - d));
+      const uint32_t K1 = K << 1;
+      return sub == 0 ? (K & ~K1) : sub == 1 ? (K & K1) : (K1 & ~K);
+    };
+    if (tid == 0 && (n0 != 16 || 3 * rows * 4 > L.nsm * L.vec_stride * 8)) os.use_flat = 0;
+    else if (tid == 0) {
       int off = 0;
       for (int e = 0; e < E; ++e) {
         const int r = os.reach[e], w = 2 * r + 1;
-        for (int a = 0; a <= r; ++a) {
-          os.loff[e][a] = off;
-          for (int x = 0; x < w; ++x) {
-            const unsigned m = dzm[os.doff[e] + a * w + x];
-            rowoff[os.doff[e] + a * w + x] = off;
-            off += 2 * __popc(m) - (int)(m & 1u);
+        for (int a = 0; a <= r; ++a)
+          for (int sub = 0; sub < 3; ++sub) {
+            const int start = off;
+            for (int x = 0; x < w; ++x) {
+              const int row = os.doff[e] + a * w + x;
+              rowoff[sub * rows + row] = off;
+              off += __popc(sub_bits(dzm[row], sub));
+            }
+            off += off & 1;
+            os.loff[e][a][sub] = (uint16_t)(start < 65535 ? start : 65535);
+            os.lcnt[e][a][sub] = (uint16_t)(off - start < 65535 ? off - start : 65535);
           }
-          off += off & 1;
-          os.lcnt[e][a] = off - os.loff[e][a];
-        }
       }
-      os.use_flat = (n0 == 16 && off <= L.list_cap) ? 1 : 0;
+      os.use_flat = (off <= L.list_cap && off < 65535) ? 1 : 0;
       PB_DCHECK(off <= L.list_cap || os.use_flat == 0, kDbgRpsmList);
     }
     __syncthreads();
     if (os.use_flat) {
       uint2* list = reinterpret_cast<uint2*>(smem_raw + L.list_off);
-      for (int t = tid; t < os.doff[E]; t += T) {
+      for (int t = tid; t < rows; t += T) {
         int e = 0;
         while (t >= os.doff[e + 1]) ++e;
         const int r = os.reach[e], w = 2 * r + 1, local = t - os.doff[e];
         const int ox = local % w - r, a = local / w;
-        const unsigned m = dzm[t];
-        int o = rowoff[t];
-        for (int k = -15; k <= 15; ++k)
-          if ((m >> (k < 0 ? -k : k)) & 1u)
-            list[o++] = make_uint2((uint32_t)((ox + 8) | ((k + 8) << 8)), (uint32_t)((k * 16 + ox) * 8));
-        if (local % w == w - 1 && ((o - os.loff[e][a]) & 1)) list[o] = make_uint2(0x3030u, 0u);   // padding
+        for (int sub = 0; sub < 3; ++sub) {
+          const uint32_t bits = sub_bits(dzm[t], sub);
+          int o = rowoff[sub * rows + t];
+          for (int b = 0; b < 32; ++b)
+            if ((bits >> b) & 1u) {
+              const int k = b - 15;
+              list[o++] = make_uint2((uint32_t)((ox + 8) + (k + 8) * 256), (uint32_t)((k * 16 + ox) * 8));
+            }
+          if (local % w == w - 1 && ((o - (int)os.loff[e][a][sub]) & 1)) list[o] = make_uint2(0x3030u, 0u);   // padding
+        }
       }
+    }
+    // the fast form's 64 warp tasks, interior first
+    for (int u = tid; u < 64; u += T) {
+      auto key = [](int w) { return abs(2 * (w >> 2) - 15) + abs(8 * (w & 3) - 12); };
+      const int ku = key(u);
+      int rank = 0;
+      for (int w = 0; w < 64; ++w) {
+        const int kw = key(w);
+        rank += (kw < ku) || (kw == ku && w < u);
+      }
+      os.pair_order[rank] = (uint8_t)u;
     }
     __syncthreads();
   }
@@ -1142,7 +1316,7 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
   // all threads: wait until group g of slot si of frame fr is in the stage
   auto stage_acquire = [&](int fr, int si, int g) {
     const long long tag = ((long long)fr << 16) | ((long long)si << 8) | (long long)g;
-    if (os.stage_tag != tag) {   // block-uniform: cold start, or a redo pass
+    if (os.stage_tag != tag) {   // block-uniform: cold start
       if (os.stage_seq > 0) oc_mbar_wait(mbar, (os.stage_seq - 1) & 1u);   // drain the copy in flight
       __syncthreads();
       if (tid == 0) stage_issue(fr, si, g);
@@ -1159,7 +1333,7 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
       for (int k = 0; k < 6; ++k) s.aff[tid][k] = p.box_affine[((size_t)f * V + tid) * 6 + k];
     }
     if (tid < E) s.limb[tid] = p.limb[(size_t)f * E + tid];
-    if (tid == 0) { os.nonfinite = 0; os.skip_ok = 1; os.redo = 0; }
+    if (tid == 0) os.nonfinite = 0;
     __syncthreads();
     const double centre[3] = {p.root[3 * (size_t)f], p.root[3 * (size_t)f + 1], p.root[3 * (size_t)f + 2]};
 
@@ -1184,125 +1358,152 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
     }
     // (every thread reads back only the coordinates it wrote itself: no barrier needed)
 
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int oi = 0; oi < os.nops; ++oi) {
-        const OcOp op = os.ops[oi];
-        double* D = vec(op.dst);
-        if (op.kind != kOpAcc) {   // sample the unary of op.joint: float64 sum over views, in order
-          double u[kOcMaxPer];
+    for (int oi = 0; oi < os.nops; ++oi) {
+      const OcOp op = os.ops[oi];
+      double* D = vec(op.dst);
+      if (op.kind != kOpAcc) {   // sample the unary of op.joint: float64 sum over views, in order
+        double u[kOcMaxPer];
 #pragma unroll
-          for (int k = 0; k < kOcMaxPer; ++k) u[k] = 0.0;
-          const int W = p.W;
-          if (ngroups > 0) {
-            for (int g = 0; g < ngroups; ++g) {
-              stage_acquire(f, op.samp, g);
-              const int v0 = g * L.stage_views, v1 = min(V, v0 + L.stage_views);
-#pragma unroll
-              for (int k = 0; k < kOcMaxPer; ++k) {
-                const int sl = tid + k * T;
-                if (sl < nb0)
-                  for (int v = v0; v < v1; ++v) {
-                    const double2 fr = __ldcg(reinterpret_cast<const double2*>(coords + ((size_t)v * nb0 + sl) * 2));
-                    const int pos = __ldcg(tappos + (size_t)v * nb0 + sl);
-                    const float* m = stage + (size_t)(v - v0) * HWm;
-                    u[k] = u[k] + bilinear_apply([m](int t) { return m[t]; }, W, pos, fr.x, fr.y);
-                  }
-              }
-              __syncthreads();   // every thread is done with the stage
-              if (tid == 0) {    // request what is needed next: it lands under the max-product below
-                if (g + 1 < ngroups) stage_issue(f, op.samp, g + 1);
-                else if (op.samp + 1 < os.nsamp) stage_issue(f, op.samp + 1, 0);
-                else if (f + (int)gridDim.x < p.B) stage_issue(f + (int)gridDim.x, 0, 0);
-              }
-              if (g + 1 < ngroups) __syncthreads();
-            }
-          } else {
+        for (int k = 0; k < kOcMaxPer; ++k) u[k] = 0.0;
+        const int W = p.W;
+        if (ngroups > 0) {
+          for (int g = 0; g < ngroups; ++g) {
+            stage_acquire(f, op.samp, g);
+            const int v0 = g * L.stage_views, v1 = min(V, v0 + L.stage_views);
 #pragma unroll
             for (int k = 0; k < kOcMaxPer; ++k) {
               const int sl = tid + k * T;
               if (sl < nb0)
-                for (int v = 0; v < V; ++v) {
+                for (int v = v0; v < v1; ++v) {
                   const double2 fr = __ldcg(reinterpret_cast<const double2*>(coords + ((size_t)v * nb0 + sl) * 2));
                   const int pos = __ldcg(tappos + (size_t)v * nb0 + sl);
-                  const float* m = p.hm + (((size_t)f * V + v) * J + op.joint) * (size_t)HWm;
-                  u[k] = u[k] + bilinear_apply([m](int t) { return __ldg(m + t); }, W, pos, fr.x, fr.y);
+                  const float* m = stage + (size_t)(v - v0) * HWm;
+                  u[k] = u[k] + bilinear_apply([m](int t) { return m[t]; }, W, pos, fr.x, fr.y);
                 }
             }
+            __syncthreads();   // every thread is done with the stage
+            if (tid == 0) {    // request what is needed next: it lands under the max-product below
+              if (g + 1 < ngroups) stage_issue(f, op.samp, g + 1);
+              else if (op.samp + 1 < os.nsamp) stage_issue(f, op.samp + 1, 0);
+              else if (f + (int)gridDim.x < p.B) stage_issue(f + (int)gridDim.x, 0, 0);
+            }
+            if (g + 1 < ngroups) __syncthreads();
           }
+        } else {
 #pragma unroll
           for (int k = 0; k < kOcMaxPer; ++k) {
             const int sl = tid + k * T;
-            if (sl < nb0) {
-              if (!(fabs(u[k]) <= 1.79769313486231570e308)) os.nonfinite = 1;   // inf / NaN: no shortcuts
-              D[sl] = u[k];   // slot order IS the memory order of the energy vectors
-            }
+            if (sl < nb0)
+              for (int v = 0; v < V; ++v) {
+                const double2 fr = __ldcg(reinterpret_cast<const double2*>(coords + ((size_t)v * nb0 + sl) * 2));
+                const int pos = __ldcg(tappos + (size_t)v * nb0 + sl);
+                const float* m = p.hm + (((size_t)f * V + v) * J + op.joint) * (size_t)HWm;
+                u[k] = u[k] + bilinear_apply([m](int t) { return __ldg(m + t); }, W, pos, fr.x, fr.y);
+              }
           }
         }
-        if (op.kind != kOpLeaf) {
-          double* S = vec(op.src);
-          if (tid == 0) os.unit_next = 0;
-          __syncthreads();
-          const int e = op.edge;
-          const bool finite = os.nonfinite == 0;
-          const bool flat = finite && os.use_flat != 0 && op.src < L.nsm && op.dst < L.nsm;
-          const bool skip_ok = pass == 0 && os.skip_ok != 0 && finite;
-          const uint32_t* row0 = p.pair_bits + (size_t)e * nb0 * words0;
-          bool bad = false;
-          for (;;) {
-            int t = 0;
-            if (lane == 0) t = atomicAdd(&os.unit_next, 1);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            if (t >= nunits) break;
-            const int u = os.unit_order[t];
-            PB_DCHECK(u >= 0 && u < nunits, kDbgRpsmUnit);
-            if (flat)   // everything on chip, every lane walks the edge's offset list
-              bad |= oc_maxprod_unit_flat(vec_s + (uint32_t)((size_t)op.src * L.vec_stride * 8),
-                                          vec_s + (uint32_t)((size_t)op.dst * L.vec_stride * 8), bp + (size_t)e * nb0,
-                                          list_s, os.loff[e], os.lcnt[e], row0, os.reach[e], u, skip_ok);
-            else
-              bad |= oc_maxprod_unit_exact(S, D, bp + (size_t)e * nb0, dzm + os.doff[e], row0, n0, nb0, os.reach[e],
-                                           u, skip_ok);
+#pragma unroll
+        for (int k = 0; k < kOcMaxPer; ++k) {
+          const int sl = tid + k * T;
+          if (sl < nb0) {
+            if (!(fabs(u[k]) <= 1.79769313486231570e308)) os.nonfinite = 1;   // inf / NaN: no shortcuts
+            D[sl] = u[k];   // slot order IS the memory order of the energy vectors
           }
-          if (bad) os.nonfinite = 1;
         }
-        __syncthreads();
       }
-
-      // ---- root argmax (first maximum) and back-tracking ----------------------------------------
-      {
-        const double* er = vec(os.root_buf);
-        double best = -INFINITY;
-        int bidx = 0x7fffffff;
-        for (int m = tid; m < nb0; m += T) {   // memory order; the first maximum is by LOGICAL index
-          const double v = er[m];
-          const int l = slot_bin(m);
-          if (bidx == 0x7fffffff || v > best || (v == best && l < bidx)) { best = v; bidx = l; }
-        }
-        warp_first_max(best, bidx);
-        if (lane == 0) { s.red_val[warp] = best; s.red_idx[warp] = bidx; }
+      if (op.kind != kOpLeaf) {
+        double* S = vec(op.src);
+        if (tid == 0) os.unit_next = 0;
         __syncthreads();
-        if (tid == 0) {
-          for (int w = 1; w < T / 32; ++w)
-            if (s.red_val[w] > best || (s.red_val[w] == best && s.red_idx[w] < bidx)) {
-              best = s.red_val[w];
-              bidx = s.red_idx[w];
+        const int e = op.edge;
+        // The child's vector is final: keep a copy for the back-tracking, which asks for the argmax of ONE
+        // parent bin per edge once the pose is known (the stores drain underneath the max-product).
+        {
+          double* keep = sfin + (size_t)e * L.vec_stride;
+#pragma unroll
+          for (int k = 0; k < kOcMaxPer; ++k) {
+            const int sl = tid + k * T;
+            if (sl < nb0) __stcg(keep + sl, S[sl]);
+          }
+        }
+        const bool finite = os.nonfinite == 0;
+        const bool flat = finite && os.use_flat != 0 && op.src < L.nsm && op.dst < L.nsm;
+        const uint32_t* row0 = p.pair_bits + (size_t)e * nb0 * words0;
+        bool bad = false;
+        for (;;) {
+          int t = 0;
+          if (lane == 0) t = atomicAdd(&os.unit_next, 1);
+          t = __shfl_sync(0xffffffffu, t, 0);
+          if (t >= (flat ? 64 : nunits)) break;
+          const int u = flat ? os.pair_order[t] : os.unit_order[t];
+          PB_DCHECK(u >= 0 && u < (flat ? 64 : nunits), kDbgRpsmUnit);
+          if (flat)   // everything on chip, every lane walks the edge's offset list
+            bad |= oc_maxprod_unit_flat(vec_s + (uint32_t)((size_t)op.src * L.vec_stride * 8),
+                                        vec_s + (uint32_t)((size_t)op.dst * L.vec_stride * 8), list_s,
+                                        os.loff[e], os.lcnt[e], row0, os.reach[e], u);
+          else
+            bad |= oc_maxprod_unit_exact(S, D, dzm + os.doff[e], row0, n0, nb0, os.reach[e], u, finite);
+        }
+        if (bad) os.nonfinite = 1;
+      }
+      __syncthreads();
+    }
+
+    // ---- root argmax (first maximum), then back-tracking level by level, one warp per edge ---------
+    {
+      const double* er = vec(os.root_buf);
+      double best = -INFINITY;
+      int bidx = 0x7fffffff;
+      for (int m = tid; m < nb0; m += T) {   // memory order; the first maximum is by LOGICAL index
+        const double v = er[m];
+        const int l = slot_bin(m);
+        if (bidx == 0x7fffffff || v > best || (v == best && l < bidx)) { best = v; bidx = l; }
+      }
+      warp_first_max(best, bidx);
+      if (lane == 0) { s.red_val[warp] = best; s.red_idx[warp] = bidx; }
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < T / 32; ++w)
+          if (s.red_val[w] > best || (s.red_val[w] == best && s.red_idx[w] < bidx)) {
+            best = s.red_val[w];
+            bidx = s.red_idx[w];
+          }
+        s.bin[p.root_idx] = bidx;
+      }
+      __syncthreads();
+      // parents before children; up to four edges of one depth at a time, eight warps (256 rows) each
+      constexpr int kGroup = 8, kGroups = T / 32 / kGroup;
+      const int g = warp / kGroup, tg = tid - g * (kGroup * 32);
+      for (int d = 1; d <= os.max_depth; ++d)
+        for (int c = os.bt_start[d]; c < os.bt_start[d + 1]; c += kGroups) {
+          const bool on = c + g < os.bt_start[d + 1];
+          const int e = on ? os.bt_edge[c + g] : 0;
+          const int par = s.bin[s.edge_p[e]];
+          if (on) {
+            const int r = os.reach[e], ww = (2 * r + 1) * (2 * r + 1);
+            OcPick a;
+            a.best = -INFINITY; a.first_v = 0.0; a.found = -1; a.first = 0x7fffffff;
+            for (int t = tg; t < ww; t += kGroup * 32) {
+              const OcPick b = oc_pick_row(sfin + (size_t)e * L.vec_stride, dzm + os.doff[e], n0, r, par, t);
+              oc_pick_merge(a, b.best, b.found, b.first_v, b.first);
             }
-          s.bin[p.root_idx] = bidx;
-          int redo = 0;
-          for (int oi = J - 1; oi >= 0; --oi) {   // parents before children
-            const int par = s.order[oi];
-            for (int ce = os.child_start[par]; ce < os.child_start[par + 1]; ++ce) {
-              const int e = os.child_edge[ce];
-              int b = bp[(size_t)e * nb0 + (n0 == 16 ? oc_swap(s.bin[par]) : s.bin[par])];   // stored by memory index
-              if (b == 0xffff) { redo = 1; b = 0; }
+            oc_pick_reduce<32>(a);
+            if (lane == 0) { os.bt_val[warp] = a.best; os.bt_idx[warp] = a.found; os.bt_fval[warp] = a.first_v; os.bt_fidx[warp] = a.first; }
+          }
+          __syncthreads();
+          if (on && warp == g * kGroup) {
+            OcPick a;
+            const int w8 = g * kGroup + (lane & (kGroup - 1));
+            a.best = os.bt_val[w8]; a.found = os.bt_idx[w8]; a.first_v = os.bt_fval[w8]; a.first = os.bt_fidx[w8];
+            oc_pick_reduce<kGroup>(a);
+            if (lane == 0) {
+              const int b = oc_pick_finish(a, p.pair_bits + (size_t)e * nb0 * words0, n0, nb0, par);
+              PB_DCHECK(b >= 0 && b < nb0, kDbgRpsmArg);
               s.bin[s.edge_c[e]] = b;
             }
           }
-          os.redo = redo;
+          __syncthreads();
         }
-        __syncthreads();
-      }
-      if (!os.redo) break;   // block-uniform
     }
 
     if (tid < J) {
@@ -1417,7 +1618,7 @@ static size_t onchip_workspace_bytes(int blocks, int V, int J, int nb0, int n0, 
   size_t b = align_up((size_t)blocks * V * nb0 * 2 * sizeof(double), 256);
   b += align_up((size_t)blocks * V * nb0 * sizeof(int32_t), 256);
   b += align_up((size_t)blocks * nspill * vec_stride * sizeof(double), 256);
-  b += align_up((size_t)blocks * (J - 1) * nb0 * sizeof(uint16_t), 256);
+  b += align_up((size_t)blocks * (J - 1) * vec_stride * sizeof(double), 256);
   return b;
 }
 
@@ -1524,7 +1725,7 @@ extern "C" int pb200_rpsm(const float* hm, int B, int V, int J, int H, int W, co
     w += align_up((size_t)blocks * V * nb0 * sizeof(int32_t), 256);
     L.spill_ws = reinterpret_cast<double*>(w);
     w += align_up((size_t)blocks * L.nspill * L.vec_stride * sizeof(double), 256);
-    L.bp_ws = reinterpret_cast<uint16_t*>(w);
+    L.sfin_ws = reinterpret_cast<double*>(w);
     static PerDevice<size_t> attr_set;
     size_t* have = attr_set.slot();
     if (have == nullptr) return PB200_ERR_CUDA;
