@@ -755,7 +755,7 @@ __device__ void oc_build_program(OcShared& os, int J, int E, int root_idx, int n
 // heatmap samples; what is left for warp 0 is a table-driven max-product over 8-bin vectors.
 template <int T>
 __device__ __forceinline__ void refine_levels8(const RpsmParams& p, OcShared& os, int f, double* gp,
-                                               double* eR, double* sv, uint8_t* bpR) {
+                                               double* eR, double* sv, double* msgR, uint8_t* bpR) {
   RpsmShared& s = os.base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int J = p.J, E = J - 1, V = p.V;
@@ -789,36 +789,41 @@ __device__ __forceinline__ void refine_levels8(const RpsmParams& p, OcShared& os
         eR[t] = u;
       }
       __syncwarp();
-      const int i = lane >> 2, q = lane & 3;   // lanes = (parent bin i) x (child bins 2q, 2q+1)
-      for (int oi = 0; oi < J; ++oi) {
-        const int par = s.order[oi];
-        const int c0 = os.child_start[par], c1 = os.child_start[par + 1];
-        if (c0 == c1) continue;
-        double acc = eR[par * 8 + i];
-        for (int ce = c0; ce < c1; ++ce) {
-          const int e = os.child_edge[ce], c = s.edge_c[e];
-          const unsigned pm = os.pmask[e * 8 + i];
-          double best = 0.0;
-          int bidx = -1;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int jj = 2 * q + h;
-            const double val = ((pm >> jj) & 1u) ? eR[c * 8 + jj] : 0.0;
-            if (bidx < 0 || val > best) { best = val; bidx = jj; }
+      // Max-product by tree depth, deepest edges first, up to four edges of a depth at a time:
+      // lanes = (edge slot) x (bin).  An edge's child vector is final once the messages of the child's own
+      // children (one depth down, already computed) are multiplied in, in edge order (pictorial.py:44-56).
+      const int i = lane & 7, sl = lane >> 3;
+      for (int d = os.max_depth; d >= 1; --d)
+        for (int c0 = os.bt_start[d]; c0 < os.bt_start[d + 1]; c0 += 4) {
+          const bool on = c0 + sl < os.bt_start[d + 1];
+          const int e = on ? os.bt_edge[c0 + sl] : 0, c = s.edge_c[e];
+          if (on) {
+            double acc = eR[c * 8 + i];
+            for (int ce = os.child_start[c]; ce < os.child_start[c + 1]; ++ce) acc = acc * msgR[os.child_edge[ce] * 8 + i];
+            eR[c * 8 + i] = acc;
           }
+          __syncwarp();
+          if (on) {   // message to parent bin i: the first maximum over the allowed child bins
+            const unsigned pm = os.pmask[e * 8 + i];
+            double best = 0.0;
+            int bidx = -1;
 #pragma unroll
-          for (int o = 1; o <= 2; o <<= 1) {  // merge the 4 lanes of this parent bin
-            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int ob = __shfl_xor_sync(0xffffffffu, bidx, o);
-            if (ov > best || (ov == best && ob < bidx)) { best = ov; bidx = ob; }
+            for (int jj = 0; jj < 8; ++jj) {
+              const double val = ((pm >> jj) & 1u) ? eR[c * 8 + jj] : 0.0;
+              if (bidx < 0 || val > best) { best = val; bidx = jj; }
+            }
+            msgR[e * 8 + i] = best;
+            bpR[e * 8 + i] = (uint8_t)bidx;
           }
-          acc = acc * best;
-          if (q == 0) bpR[e * 8 + i] = (uint8_t)bidx;
+          __syncwarp();
         }
-        __syncwarp();
-        if (q == 0) eR[par * 8 + i] = acc;
-        __syncwarp();
+      if (lane < 8) {
+        const int c = p.root_idx;
+        double acc = eR[c * 8 + lane];
+        for (int ce = os.child_start[c]; ce < os.child_start[c + 1]; ++ce) acc = acc * msgR[os.child_edge[ce] * 8 + lane];
+        eR[c * 8 + lane] = acc;
       }
+      __syncwarp();
       if (lane == 0) {
         const double* er = eR + p.root_idx * 8;
         double best = er[0];
@@ -826,15 +831,15 @@ __device__ __forceinline__ void refine_levels8(const RpsmParams& p, OcShared& os
         for (int b = 1; b < 8; ++b)
           if (er[b] > best) { best = er[b]; bidx = b; }
         s.bin[p.root_idx] = bidx;
-        for (int oi = J - 1; oi >= 0; --oi) {
-          const int par = s.order[oi];
-          for (int ce = os.child_start[par]; ce < os.child_start[par + 1]; ++ce) {
-            const int e = os.child_edge[ce];
-            s.bin[s.edge_c[e]] = bpR[e * 8 + s.bin[par]];
-          }
-        }
       }
       __syncwarp();
+      for (int d = 1; d <= os.max_depth; ++d) {   // back-tracking: parents before children, a lane per edge
+        for (int k = os.bt_start[d] + lane; k < os.bt_start[d + 1]; k += 32) {
+          const int e = os.bt_edge[k];
+          s.bin[s.edge_c[e]] = bpR[e * 8 + s.bin[s.edge_p[e]]];
+        }
+        __syncwarp();
+      }
       if (lane < J) {
         const int b = s.bin[lane];
         if (p.out_trace) p.out_trace[((size_t)f * (p.depth + 1) + lvl) * J + lane] = b;
@@ -1157,7 +1162,8 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
   double* gp = reinterpret_cast<double*>(smem_raw + L.refine_off);
   double* eR = gp + (size_t)J * nbR_ * 3;
   double* sv = eR + (size_t)J * nbR_;
-  uint8_t* bpR = reinterpret_cast<uint8_t*>(sv + (size_t)V * J * nbR_);
+  double* msgR = sv + (size_t)V * J * nbR_;   // (refine_levels8) messages per (edge, parent bin)
+  uint8_t* bpR = reinterpret_cast<uint8_t*>(msgR + (size_t)E * nbR_);
   double* coords = L.coords_ws + (size_t)blockIdx.x * V * nb0 * 2;   // (fx, fy) of every (view, bin)
   int32_t* tappos = L.tap_ws + (size_t)blockIdx.x * V * nb0;         // top-left tap, or outside / NaN
   double* spill = L.spill_ws + (size_t)blockIdx.x * L.nspill * L.vec_stride;
@@ -1246,8 +1252,12 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
       const uint32_t K1 = K << 1;
       return sub == 0 ? (K & ~K1) : sub == 1 ? (K & K1) : (K1 & ~K);
     };
-    if (tid == 0 && (n0 != 16 || 3 * rows * 4 > L.nsm * L.vec_stride * 8)) os.use_flat = 0;
-    else if (tid == 0) {
+    const bool can = n0 == 16 && 3 * rows * 4 <= L.nsm * L.vec_stride * 8;   // block-uniform
+    if (can)
+      for (int t = tid; t < 3 * rows; t += T) rowoff[t] = __popc(sub_bits(dzm[t % rows], t / rows));   // counts ...
+    __syncthreads();
+    if (tid == 0 && !can) os.use_flat = 0;
+    else if (tid == 0) {   // ... to offsets, in list order
       int off = 0;
       for (int e = 0; e < E; ++e) {
         const int r = os.reach[e], w = 2 * r + 1;
@@ -1256,8 +1266,9 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
             const int start = off;
             for (int x = 0; x < w; ++x) {
               const int row = os.doff[e] + a * w + x;
+              const int cnt = rowoff[sub * rows + row];
               rowoff[sub * rows + row] = off;
-              off += __popc(sub_bits(dzm[row], sub));
+              off += cnt;
             }
             off += off & 1;
             os.loff[e][a][sub] = (uint16_t)(start < 65535 ? start : 65535);
@@ -1513,7 +1524,7 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
       if (p.out_trace) p.out_trace[((size_t)f * (p.depth + 1)) * J + tid] = s.bin[tid];
     }
     __syncthreads();
-    if (p.nR == 2) refine_levels8<T>(p, os, f, gp, eR, sv, bpR);
+    if (p.nR == 2) refine_levels8<T>(p, os, f, gp, eR, sv, msgR, bpR);
     else refine_levels<T>(p, s, f, gp, eR, sv, bpR);
     if (tid < J) {
       double* o = p.out_pose + ((size_t)f * J + tid) * 3;
@@ -1639,19 +1650,33 @@ static bool rpsm_onchip_layout(const float* hm, int V, int J, int H, int W, int 
   L.dzm_off = (int)off;
   L.dzm_cap = E * (max_reach + 1) * (2 * max_reach + 1);
   off = align_up(off + (size_t)L.dzm_cap * sizeof(uint16_t), 16);
-  L.refine_off = (int)off;
-  off = align_up(off + (size_t)J * nbR * (3 + 1 + V) * sizeof(double) + (size_t)E * nbR, 16);
-  L.vec_off = (int)off;
+  // the refinement's arrays (grid points, energies, samples, messages, back pointers): they are only alive
+  // between the back-tracking of a frame and the first sample of the next, when the energy vectors are dead, so
+  // they share the vectors' memory whenever they fit there (always on the reference's 16^3 grid)
+  const size_t refine_bytes =
+      align_up((size_t)J * nbR * (3 + 1 + V) * sizeof(double) + (size_t)E * nbR * sizeof(double) + (size_t)E * nbR, 16);
   L.vec_stride = (int)align_up((size_t)nb0, 2);
   const size_t vec_bytes = (size_t)L.vec_stride * sizeof(double);
-  if (off + 2 * vec_bytes > (size_t)kOcSmemBudget) return false;   // source + destination must be on chip
   const int need = onchip_max_vectors(J);
-  const int fit = (int)(((size_t)kOcSmemBudget - off) / vec_bytes);
-  // leave ~16 KiB for the child-offset lists unless that would push one of the 4 vectors the reference
-  // skeletons need off the chip
-  int nsm = (int)(((size_t)kOcSmemBudget - off - 16 * 1024) / vec_bytes);
-  if (nsm < 4) nsm = fit < 4 ? fit : 4;
-  if (nsm > need) nsm = need;
+  int nsm = 0;
+  for (int alias = 1; alias >= 0; --alias) {
+    const size_t voff = alias ? off : off + refine_bytes;
+    if (voff + 2 * vec_bytes > (size_t)kOcSmemBudget) {   // source + destination must be on chip
+      if (alias) continue;
+      return false;
+    }
+    const int fit = (int)(((size_t)kOcSmemBudget - voff) / vec_bytes);
+    // leave ~16 KiB for the child-offset lists unless that would push one of the 4 vectors the reference
+    // skeletons need off the chip
+    nsm = (int)(((size_t)kOcSmemBudget - voff - 16 * 1024) / vec_bytes);
+    if (nsm < 4) nsm = fit < 4 ? fit : 4;
+    if (nsm > need) nsm = need;
+    if (alias && (size_t)nsm * vec_bytes < refine_bytes) continue;
+    L.refine_off = (int)(alias ? voff : off);
+    off = voff;
+    break;
+  }
+  L.vec_off = (int)off;
   L.nsm = nsm;
   L.nspill = need - nsm;
   L.list_off = (int)(off + (size_t)nsm * vec_bytes);
