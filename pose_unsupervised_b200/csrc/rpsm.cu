@@ -725,15 +725,13 @@ __device__ void oc_build_program(OcShared& os, int J, int E, int root_idx, int n
   }
   os.child_start[J] = ce;
   int md = 0;
-  uint8_t depth[kRpsmMaxJ];
+  uint8_t depth[kRpsmMaxJ], up[kRpsmMaxJ];
+  for (int j = 0; j < J; ++j) up[j] = (uint8_t)root_idx;
+  for (int e = 0; e < E; ++e) up[s.edge_c[e]] = (uint8_t)s.edge_p[e];
   for (int e = 0; e < E; ++e) {
     int d = 1, j = s.edge_p[e];
     for (int guard = 0; j != root_idx && guard < E; ++guard) {
-      int up = -1;
-      for (int q = 0; q < E; ++q)
-        if (s.edge_c[q] == j) up = s.edge_p[q];
-      if (up < 0) break;
-      j = up;
+      j = up[j];
       ++d;
     }
     depth[e] = (uint8_t)d;
@@ -754,28 +752,25 @@ __device__ void oc_build_program(OcShared& os, int J, int E, int root_idx, int n
 // bin, child bin) pairs do not depend on the energies, so they are evaluated one per thread next to the
 // heatmap samples; what is left for warp 0 is a table-driven max-product over 8-bin vectors.
 template <int T>
-__device__ __forceinline__ void refine_levels8(const RpsmParams& p, OcShared& os, int f, double* gp,
-                                               double* eR, double* sv, double* msgR, uint8_t* bpR) {
+__device__ __forceinline__ void refine_levels8(const RpsmParams& p, OcShared& os, int f, double* eR, double* sv,
+                                               double* msgR, uint8_t* bpR) {
   RpsmShared& s = os.base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int J = p.J, E = J - 1, V = p.V;
   double cur = p.grid_size / (double)p.n0;
   for (int lvl = 1; lvl <= p.depth; ++lvl) {
-    for (int t = tid; t < J * 8; t += T) {
-      const int j = t >> 3, b = t & 7;
-      double X[3];
-      bin_to_point(cur, 2, b, s.pose[j], X);
-      gp[3 * t] = X[0]; gp[3 * t + 1] = X[1]; gp[3 * t + 2] = X[2];
-    }
-    __syncthreads();
+    // (a 2^3 grid point is three selects and adds: every thread makes the ones it needs, no table, no barrier)
     for (int t = tid; t < V * J * 8; t += T) {
       const int v = t / (J * 8), r = t - v * (J * 8);
-      sv[t] = sample_view(p, s, f, v, r >> 3, gp + 3 * r);
+      double X[3];
+      bin_to_point(cur, 2, r & 7, s.pose[r >> 3], X);
+      sv[t] = sample_view(p, s, f, v, r >> 3, X);
     }
     for (int t = tid; t < E * 64; t += T) {   // E * 64 is a multiple of 32: whole warps
       const int e = t >> 6, i = (t >> 3) & 7, jj = t & 7;
-      const double* gi = gp + 3 * (s.edge_p[e] * 8 + i);
-      const double* gj = gp + 3 * (s.edge_c[e] * 8 + jj);
+      double gi[3], gj[3];
+      bin_to_point(cur, 2, i, s.pose[s.edge_p[e]], gi);
+      bin_to_point(cur, 2, jj, s.pose[s.edge_c[e]], gj);
       const double dx = gi[0] - gj[0], dy = gi[1] - gj[1], dz = gi[2] - gj[2];
       const double d = sqrt((dx * dx + dy * dy) + dz * dz);
       const unsigned bal = __ballot_sync(0xffffffffu, fabs(d - s.limb[e]) <= p.tol);
@@ -843,9 +838,9 @@ __device__ __forceinline__ void refine_levels8(const RpsmParams& p, OcShared& os
       if (lane < J) {
         const int b = s.bin[lane];
         if (p.out_trace) p.out_trace[((size_t)f * (p.depth + 1) + lvl) * J + lane] = b;
-        const double* g = gp + 3 * (lane * 8 + b);
-        const double X0 = g[0], X1 = g[1], X2 = g[2];
-        s.pose[lane][0] = X0; s.pose[lane][1] = X1; s.pose[lane][2] = X2;
+        double X[3];
+        bin_to_point(cur, 2, b, s.pose[lane], X);
+        s.pose[lane][0] = X[0]; s.pose[lane][1] = X[1]; s.pose[lane][2] = X[2];
       }
     }
     __syncthreads();
@@ -1252,50 +1247,62 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
       const uint32_t K1 = K << 1;
       return sub == 0 ? (K & ~K1) : sub == 1 ? (K & K1) : (K1 & ~K);
     };
-    const bool can = n0 == 16 && 3 * rows * 4 <= L.nsm * L.vec_stride * 8;   // block-uniform
+    const bool can = n0 == 16 && 6 * rows * 4 <= L.nsm * L.vec_stride * 8;   // block-uniform
+    int32_t* pre = rowoff + 3 * rows;
+    auto row_slot = [&](int row, int& e, int& a, int& x, int& w) {   // row -> (edge, |oy|, column, columns)
+      e = 0;
+      while (row >= os.doff[e + 1]) ++e;
+      w = 2 * os.reach[e] + 1;
+      const int local = row - os.doff[e];
+      a = local / w;
+      x = local - a * w;
+    };
     if (can)
-      for (int t = tid; t < 3 * rows; t += T) rowoff[t] = __popc(sub_bits(dzm[t % rows], t / rows));   // counts ...
+      for (int t = tid; t < 3 * rows; t += T) rowoff[t] = __popc(sub_bits(dzm[t % rows], t / rows));   // entries per row
+    __syncthreads();
+    if (can)
+      for (int t = tid; t < 3 * rows; t += T) {   // a row's offset within its sub-list; the last row knows the length
+        const int sub = t / rows, row = t - sub * rows;
+        int e, a, x, w;
+        row_slot(row, e, a, x, w);
+        int before = 0;
+        for (int k = 1; k <= x; ++k) before += rowoff[t - k];
+        pre[t] = before;
+        if (x == w - 1) {
+          const int n = before + rowoff[t];
+          os.lcnt[e][a][sub] = (uint16_t)min(n + (n & 1), 65535);
+        }
+      }
     __syncthreads();
     if (tid == 0 && !can) os.use_flat = 0;
-    else if (tid == 0) {   // ... to offsets, in list order
+    else if (tid == 0) {   // the sub-lists one after the other
       int off = 0;
-      for (int e = 0; e < E; ++e) {
-        const int r = os.reach[e], w = 2 * r + 1;
-        for (int a = 0; a <= r; ++a)
+      for (int e = 0; e < E; ++e)
+        for (int a = 0; a <= os.reach[e]; ++a)
           for (int sub = 0; sub < 3; ++sub) {
-            const int start = off;
-            for (int x = 0; x < w; ++x) {
-              const int row = os.doff[e] + a * w + x;
-              const int cnt = rowoff[sub * rows + row];
-              rowoff[sub * rows + row] = off;
-              off += cnt;
-            }
-            off += off & 1;
-            os.loff[e][a][sub] = (uint16_t)(start < 65535 ? start : 65535);
-            os.lcnt[e][a][sub] = (uint16_t)(off - start < 65535 ? off - start : 65535);
+            os.loff[e][a][sub] = (uint16_t)min(off, 65535);
+            off += os.lcnt[e][a][sub];
           }
-      }
       os.use_flat = (off <= L.list_cap && off < 65535) ? 1 : 0;
       PB_DCHECK(off <= L.list_cap || os.use_flat == 0, kDbgRpsmList);
     }
     __syncthreads();
     if (os.use_flat) {
       uint2* list = reinterpret_cast<uint2*>(smem_raw + L.list_off);
-      for (int t = tid; t < rows; t += T) {
-        int e = 0;
-        while (t >= os.doff[e + 1]) ++e;
-        const int r = os.reach[e], w = 2 * r + 1, local = t - os.doff[e];
-        const int ox = local % w - r, a = local / w;
-        for (int sub = 0; sub < 3; ++sub) {
-          const uint32_t bits = sub_bits(dzm[t], sub);
-          int o = rowoff[sub * rows + t];
-          for (int b = 0; b < 32; ++b)
-            if ((bits >> b) & 1u) {
-              const int k = b - 15;
-              list[o++] = make_uint2((uint32_t)((ox + 8) + (k + 8) * 256), (uint32_t)((k * 16 + ox) * 8));
-            }
-          if (local % w == w - 1 && ((o - (int)os.loff[e][a][sub]) & 1)) list[o] = make_uint2(0x3030u, 0u);   // padding
-        }
+      for (int t = tid; t < 3 * rows; t += T) {
+        const int sub = t / rows, row = t - sub * rows;
+        int e, a, x, w;
+        row_slot(row, e, a, x, w);
+        const int ox = x - os.reach[e];
+        const uint32_t bits = sub_bits(dzm[row], sub);
+        const int o0 = os.loff[e][a][sub];
+        int o = o0 + pre[t];
+        for (int b = 0; b < 32; ++b)
+          if ((bits >> b) & 1u) {
+            const int k = b - 15;
+            list[o++] = make_uint2((uint32_t)((ox + 8) + (k + 8) * 256), (uint32_t)((k * 16 + ox) * 8));
+          }
+        if (x == w - 1 && ((o - o0) & 1)) list[o] = make_uint2(0x3030u, 0u);   // padding
       }
     }
     // the fast form's 64 warp tasks, interior first
@@ -1524,7 +1531,7 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
       if (p.out_trace) p.out_trace[((size_t)f * (p.depth + 1)) * J + tid] = s.bin[tid];
     }
     __syncthreads();
-    if (p.nR == 2) refine_levels8<T>(p, os, f, gp, eR, sv, msgR, bpR);
+    if (p.nR == 2) refine_levels8<T>(p, os, f, eR, sv, msgR, bpR);
     else refine_levels<T>(p, s, f, gp, eR, sv, bpR);
     if (tid < J) {
       double* o = p.out_pose + ((size_t)f * J + tid) * 3;
