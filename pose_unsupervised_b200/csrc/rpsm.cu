@@ -525,21 +525,25 @@ __global__ void __launch_bounds__(kRpsmThreads, 2) rpsm_kernel(const RpsmParams 
 //     memory by the copy engine (cp.async.bulk + mbarrier; the next joint's maps -- or the next
 //     frame's first -- are requested as soon as the stage is free, so the copy runs under the
 //     max-product of the current joint);
-//   * energy vectors (nb0 float64 + their row / plane maxima) live in shared memory: with the
-//     first child's message folded into the parent's unary on the fly, the two reference skeletons
-//     never need more than 4 live vectors (128 KiB); deeper trees spill the extra ones to scratch;
-//   * the max over a parent's allowed children walks rows of n0 z-bins in ascending index order and
-//     skips every row (and every y-plane) whose maximum cannot beat the best value found so far --
-//     exact: a later candidate replaces the first maximum only if it is strictly larger;
-//   * parents whose accumulated energy is exactly 0 skip the maximisation (their product is 0); if
-//     back-tracking ever lands on such a bin (all-nonpositive energies) the frame is redone without
-//     the shortcut, so results are always those of np.argmax on the full product;
-//   * only the uint16 back pointers are written to global memory.
-// Bit-identical to rpsm_kernel (tests/test_gpu_rpsm.py compares both against the reference golden).
+//   * energy vectors (nb0 float64) live in shared memory: with the first child's message folded into the
+//     parent's unary on the fly, the two reference skeletons never need more than 4 live vectors
+//     (128 KiB); deeper trees spill the extra ones to scratch;
+//   * the FORWARD pass computes only the VALUE max_j(P[i,j] ? S[j] : 0) per parent bin, which makes the
+//     maximum order-free: a lane owns two z-neighbouring parents and walks the edge's child-offset lists
+//     (children of one parent, of both, of the other), so most energies are read from shared memory once
+//     and compared twice (oc_maxprod_unit_flat);
+//   * parents whose accumulated energy is exactly 0 skip the maximisation (0 * finite = 0);
+//   * every child's final vector is also copied to an L2 scratch (E * nb0 float64 per block), and the
+//     BACK-TRACKING resolves the reference's first-argmax rule there, for the ONE parent bin per edge that
+//     lies on the chosen pose -- edges of one tree depth in parallel, 256 threads each (oc_pick_*);
+//   * the 2^3 refinement levels evaluate all limb predicates and heatmap samples one per thread, and one warp
+//     runs the 8-bin max-product by tree depth (refine_levels8); their arrays share the vectors' memory.
+// Bit-identical to rpsm_kernel (tests/test_gpu_rpsm.py compares both with each other, with the oracle and
+// with the reference's golden frames).
 // =================================================================================================
 #ifndef PB_RPSM_L2_HINTS
 #define PB_RPSM_L2_HINTS 1   // evict_first on the heatmap stream, evict_last on the parked sample taps: same speed,
-                             // DRAM bytes 1.23x instead of 1.50x the algorithmic heatmap bytes (profiles/r02_rpsm_*)
+                             // 0.27x the algorithmic heatmap bytes less DRAM traffic (profiles/r02_rpsm_*)
 #endif
 constexpr int kOcThreads = 1024;
 constexpr int kOcMaxPer = 4;                 // level-0 bins per thread: nb0 <= 4096
@@ -1305,9 +1309,10 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
         if (x == w - 1 && ((o - o0) & 1)) list[o] = make_uint2(0x3030u, 0u);   // padding
       }
     }
-    // the fast form's 64 warp tasks, interior first
+    // the fast form's 64 warp tasks, longest first: a task walks the slices |oy| its plane iy has inside the grid
+    // (z only masks lanes), so its length falls with the plane's distance from the middle
     for (int u = tid; u < 64; u += T) {
-      auto key = [](int w) { return abs(2 * (w >> 2) - 15) + abs(8 * (w & 3) - 12); };
+      auto key = [](int w) { return abs(2 * (w >> 2) - 15); };
       const int ku = key(u);
       int rank = 0;
       for (int w = 0; w < 64; ++w) {

@@ -201,12 +201,13 @@ def test_rpsm_wide_shells_take_the_sorted_walk(pict):
 
 @pytest.mark.parametrize('nviews,hw,nframes', [(4, 64, 330), (8, 64, 24), (4, 96, 24), (2, 80, 24), (3, 63, 12)])
 def test_rpsm_onchip_equals_generic_kernel(pict, nviews, hw, nframes):
-    """The on-chip level 0 (staged heatmaps, shared-memory energies, pruned max, zero shortcut) and the
-    generic kernel are two implementations of the same arithmetic: identical bins at every level and
-    identical poses.  330 frames > 2 x 148 SMs: every persistent block processes several frames, so the
+    """The on-chip level 0 (staged heatmaps, shared-memory energies, value-only max-product with two parents
+    per lane, argmax resolved during back-tracking) and the generic kernel are two implementations of the same
+    arithmetic: identical bins at every level and identical poses.  330 frames > 2 x 148 SMs: every persistent block processes several frames, so the
     cross-frame prefetch is exercised; 8 views / 96^2 / 80^2 maps need several staged groups per joint;
     63^2 maps are not 16-byte sized and are sampled with plain loads.  Degenerate frames (all-negative and
-    all-zero joints) force the redo-without-shortcut pass in the middle of the batch."""
+    all-zero joints) take the zero-energy shortcut of the forward pass and the all-nonpositive rule of the
+    back-tracking in the middle of the batch."""
     from pose_unsupervised_b200.multiviews.body import HumanBody
     body, obody = HumanBody.h36m17(), h36m17()
     edges = obody.edges()
@@ -321,3 +322,46 @@ def test_rpsm_full_batch_is_repeatable(pict):
             first = (poses.clone(), trace.clone())
         else:
             assert torch.equal(first[0], poses) and torch.equal(first[1], trace)
+
+
+def test_rpsm_nonfinite_frames_do_not_leak(pict):
+    """inf / NaN heatmaps switch THEIR frame to the per-lane enumeration (no shortcuts); what such a frame
+    answers is deterministic but unspecified (the reference's own answer is a property of numpy's NaN ordering).
+    The neighbours in the batch -- same block, same shared memory, before and after -- must answer exactly
+    what they answer in a clean batch, and two launches must agree bit for bit."""
+    from pose_unsupervised_b200.multiviews.body import HumanBody
+    body, obody = HumanBody.h36m17(), h36m17()
+    edges = obody.edges()
+    cfg = rpsm_config(depth=3)
+    avg = {e: float(np.mean([np.linalg.norm(p[e[0]] - p[e[1]]) for p in synth.random_poses(64, seed=99)]))
+           for e in edges}
+    table = pict.PairwiseTable.from_limb_lengths(avg, body, 2000, 16)
+    nframes, base = 320, 5                                # > 2 frames per persistent block
+    frames = [_frame(edges, 17, 700 + f) for f in range(base)]
+    pick = np.arange(nframes) % base
+    hms = np.array([frames[i][3] for i in pick])
+    cams = [c for i in pick for c in frames[i][1]]
+    centers = np.array([b['center'] for i in pick for b in frames[i][2]])
+    scales = np.array([b['scale'] for i in pick for b in frames[i][2]])
+    roots = np.array([frames[i][0][0] for i in pick])
+    limbs = np.array([[frames[i][4][e] for e in edges] for i in pick])
+    clean, clean_t = pict.rpsm_batch(cams, hms, centers, scales, roots, limbs, table, cfg, body, return_trace=True)
+    dirty = hms.copy()
+    bad = np.arange(3, nframes, 7)
+    for n, f in enumerate(bad):
+        if n % 3 == 0:
+            dirty[f, 0, 4, 10:20, 10:20] = np.inf         # overflow: inf, then inf * 0 = NaN further up the tree
+        elif n % 3 == 1:
+            dirty[f, 1, 9, 30, 30] = np.nan
+        else:
+            dirty[f, 2, 0] = -np.inf
+    runs = [pict.rpsm_batch(cams, dirty, centers, scales, roots, limbs, table, cfg, body, return_trace=True)
+            for _ in range(2)]
+    good = np.setdiff1d(np.arange(nframes), bad)
+    for poses, trace in runs:
+        assert np.array_equal(np.asarray(poses)[good], np.asarray(clean)[good])
+        assert np.array_equal(np.asarray(trace)[good], np.asarray(clean_t)[good])
+        t = np.asarray(trace)[bad]
+        assert t.min() >= 0 and t[:, 0].max() < 16 ** 3 and t[:, 1:].max() < 8   # bins stay inside their grids
+    assert np.array_equal(np.asarray(runs[0][0]), np.asarray(runs[1][0]), equal_nan=True)
+    assert np.array_equal(np.asarray(runs[0][1]), np.asarray(runs[1][1]))
