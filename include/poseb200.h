@@ -74,7 +74,7 @@ int pb200_crop_affine(const void* center, int center_dtype, const void* scale, i
 /* ---- debug-assert build ---------------------------------------------------------------
  * A library compiled with -DPB200_DEBUG_CHECKS=1 (python -m pose_unsupervised_b200.build --debug ->
  * libposeb200_debug.so) makes the kernels check the invariants their hand-offs rely on (map indices and
- * counts of the decode schedule, candidate addresses / back pointers / task indices / stage contents of the
+ * counts of the decode schedule, candidate addresses / back-tracked bins / task indices / stage contents of the
  * on-chip RPSM, item indices of RANSAC).  pb200_debug_enabled() is 1 for such a build;
  * pb200_debug_violations synchronises the device and copies the 16 violation counters (all zero in a
  * release build), optionally resetting them.  Stands in for compute-sanitizer, which the GPU pool does
@@ -287,8 +287,9 @@ int pb200_lift_decoded(const double* campack, const int32_t* cam_index, const fl
  *   max_reach : out_flag[1] of pb200_pairwise_lut_check (largest |bin offset| of an allowed pair),
  *             or -1 if unknown.  With use_lut = 1, max_reach in [0, 5] and first_nbins <= 16 level 0
  *             runs entirely on chip (heatmaps staged in shared memory by cp.async.bulk, energies in
- *             shared memory, only uint16 back pointers written out); any other combination takes
- *             the generic kernel.  Both give identical results.
+ *             shared memory; each joint's final energy vector is also kept in the workspace for the
+ *             back-tracking); any other combination takes the generic kernel.  Both give identical
+ *             results.
  *   workspace : bytes from pb200_rpsm_workspace_bytes, 256-byte aligned
  *   out_pose  [B,J,3] float64 ; out_trace [B, depth+1, J] int32 chosen bin per level (or NULL)
  */

@@ -67,7 +67,7 @@ enum {
   kDbgDecodeMapRange = 0,     // a decode warp was handed a map index outside [0, total)
   kDbgDecodeMapCount = 1,     // maps decoded in one launch != N*J
   kDbgRpsmCandAddr = 2,       // an in-grid candidate address outside the source vector
-  kDbgRpsmArg = 3,            // a back pointer outside [0, nbins)
+  kDbgRpsmArg = 3,            // a back-tracked bin outside [0, nbins)
   kDbgRpsmUnit = 4,           // a warp task index outside [0, nunits)
   kDbgRpsmStage = 5,          // the stage was read while it held another (frame, joint, group)
   kDbgRpsmList = 6,           // the offset lists overflow their shared-memory area

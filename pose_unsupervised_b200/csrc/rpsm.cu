@@ -884,16 +884,11 @@ __device__ __forceinline__ double oc_lds64(uint32_t a) {
 __device__ __forceinline__ void oc_sts64(uint32_t a, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
-__device__ __forceinline__ unsigned oc_lds16(uint32_t a) {
-  unsigned v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-  return v;
-}
 // Energy vectors of the on-chip kernel are stored x-FASTEST on the 16^3 grid: memory index m = (iy, iz, ix),
 // i.e. the logical bin index (iy, ix, iz) of pictorial.py:108-119 with its two low nibbles swapped.  The unary
 // samples arrive with lanes along grid x (fewer shared-memory bank conflicts when reading the staged maps, see
 // the sampling loop), so they are stored with unit stride, and the max-product walks along x just as well as
-// along z.  Everything visible outside the kernel (back pointers, traces, poses) uses logical indices.
+// along z.  Everything visible outside the kernel (traces, poses) uses logical indices.
 __device__ __forceinline__ int oc_swap(int j) { return (j & ~0xff) | ((j & 15) << 4) | ((j >> 4) & 15); }
 
 __device__ __forceinline__ uint4 oc_lds128(uint32_t a) {
