@@ -551,6 +551,7 @@ constexpr int kOcMaxOps = 2 * kRpsmMaxJ;
 constexpr int kOcMaxUnits = kOcMaxPer * kOcThreads / 32;   // warp tasks of 32 consecutive parent bins
 constexpr int kOcStageBytes = 64 * 1024;
 constexpr int kOcSmemBudget = 227 * 1024;
+constexpr int kOcRefineSteps = 12;           // refinement schedule: (depth, four edges) steps / tree depths it can hold
 
 enum { kOpLeaf = 0, kOpFirst = 1, kOpAcc = 2 };
 struct OcOp {
@@ -589,6 +590,13 @@ struct OcShared {
   uint8_t bt_edge[kRpsmMaxJ];   // edges sorted by the tree depth of their child joint (root's children: 1) ...
   uint8_t bt_start[kRpsmMaxJ + 2];   // ... and where depth d starts in that list: the back-tracking order
   int max_depth;
+  // refinement (refine_levels8): what every lane of warp 0 does in each step of the 8-bin max-product and of its
+  // back-tracking, precomputed so that the tables' walk is not a chain of dependent shared-memory reads
+  uint2 rstep[kOcRefineSteps][32];     // x = edge | child joint << 8 | #children of the child << 16 | active << 24,
+                                       // y = the edges of those children (4 x 8 bits)
+  uint32_t rback[kOcRefineSteps][32];  // per tree depth: edge | parent joint << 8 | child joint << 16 | active << 24
+  uint32_t rroot;                      // the root's child edges (4 x 8 bits)
+  int rsteps, rroot_n;                 // steps in rstep (-1: the tree does not fit the tables); children of the root
   double bt_val[kOcThreads / 32], bt_fval[kOcThreads / 32];   // back-tracking: per-warp partial results
   int bt_idx[kOcThreads / 32], bt_fidx[kOcThreads / 32];
   unsigned long long mbar;
@@ -653,10 +661,20 @@ __device__ __forceinline__ void oc_bulk_g2s(uint32_t dst, const void* src, uint3
 #endif
 }
 
+// Offsets of the edges' |dz| tables (thread 0, once the shell reach of every edge is known).
+__device__ void oc_table_offsets(OcShared& os, int E) {
+  int off = 0;
+  for (int e = 0; e < E; ++e) {
+    os.doff[e] = off;
+    off += (os.reach[e] + 1) * (2 * os.reach[e] + 1);   // rows |oy| = 0..r, columns ox = -r..r
+  }
+  os.doff[E] = off;
+}
+
 // Depth-first program (thread 0, once per block).  LEAF: dst = unary(joint).  FIRST: dst = unary(joint) *
 // msg(edge, src).  ACC: dst *= msg(edge, src).  Children in edge-array order, which is the order the
 // reference multiplies them in (pictorial.py:44-56).  Buffers are numbered so that the low ids (shared
-// memory) are reused first.  Also: child lists per joint (CSR) and the offsets of the |dz| table.
+// memory) are reused first.  Also: child lists per joint (CSR) and the edges sorted by tree depth.
 __device__ void oc_build_program(OcShared& os, int J, int E, int root_idx, int nbuf) {
   const RpsmShared& s = os.base;
   struct Frame { int node, pos, acc, pending; };
@@ -716,12 +734,7 @@ __device__ void oc_build_program(OcShared& os, int J, int E, int root_idx, int n
   os.nsamp = nsamp;
   os.root_buf = ret < 0 ? 0 : ret;
   os.prog_err = err;
-  int off = 0, ce = 0;
-  for (int e = 0; e < E; ++e) {
-    os.doff[e] = off;
-    off += (os.reach[e] + 1) * (2 * os.reach[e] + 1);   // rows |oy| = 0..r, columns ox = -r..r
-  }
-  os.doff[E] = off;
+  int ce = 0;
   for (int j = 0; j < J; ++j) {
     os.child_start[j] = ce;
     for (int e = 0; e < E; ++e)
@@ -749,6 +762,43 @@ __device__ void oc_build_program(OcShared& os, int J, int E, int root_idx, int n
       if (depth[e] == d) os.bt_edge[pos++] = (uint8_t)e;
   }
   os.bt_start[md + 1] = (uint8_t)pos;
+}
+
+// Schedule of refine_levels8's warp 0 (built by warp 0 once per block, after oc_build_program): step = (tree
+// depth, deepest first) x (four edges of that depth), lanes = (edge slot) x (bin).
+__device__ void oc_refine_schedule(OcShared& os, int J, int E, int root_idx) {
+  const RpsmShared& s = os.base;
+  const int lane = threadIdx.x & 31, sl = lane >> 3;
+  int st = 0;
+  bool fit = os.max_depth <= kOcRefineSteps;
+  for (int d = os.max_depth; d >= 1; --d)
+    for (int c0 = os.bt_start[d]; c0 < os.bt_start[d + 1]; c0 += 4, ++st) {
+      if (st >= kOcRefineSteps) continue;
+      const bool on = c0 + sl < os.bt_start[d + 1];
+      const int e = on ? os.bt_edge[c0 + sl] : 0, c = s.edge_c[e];
+      const int k0 = os.child_start[c], nch = on ? os.child_start[c + 1] - k0 : 0;
+      if (nch > 4) fit = false;
+      uint32_t ch = 0u;
+      for (int k = 0; k < nch && k < 4; ++k) ch |= (uint32_t)os.child_edge[k0 + k] << (8 * k);
+      os.rstep[st][lane] = make_uint2((uint32_t)e | ((uint32_t)c << 8) | ((uint32_t)nch << 16) | ((on ? 1u : 0u) << 24), ch);
+    }
+  for (int d = 1; d <= os.max_depth && d <= kOcRefineSteps; ++d) {
+    const int k = os.bt_start[d] + lane;
+    const bool on = k < os.bt_start[d + 1];
+    const int e = on ? os.bt_edge[k] : 0;
+    os.rback[d - 1][lane] = (uint32_t)e | ((uint32_t)s.edge_p[e] << 8) | ((uint32_t)s.edge_c[e] << 16) | ((on ? 1u : 0u) << 24);
+    if (os.bt_start[d + 1] - os.bt_start[d] > 32) fit = false;
+  }
+  const int r0 = os.child_start[root_idx], rn = os.child_start[root_idx + 1] - r0;
+  if (rn > 4 || st > kOcRefineSteps) fit = false;
+  fit = __all_sync(0xffffffffu, fit);
+  if (lane == 0) {
+    uint32_t ch = 0u;
+    for (int k = 0; k < rn && k < 4; ++k) ch |= (uint32_t)os.child_edge[r0 + k] << (8 * k);
+    os.rroot = ch;
+    os.rroot_n = rn;
+    os.rsteps = fit ? st : -1;
+  }
 }
 
 // ---- refinement levels for 2^3 grids (the reference's RECUR_NBINS = 2), block-wide ------------------
@@ -791,7 +841,58 @@ __device__ __forceinline__ void refine_levels8(const RpsmParams& p, OcShared& os
       // Max-product by tree depth, deepest edges first, up to four edges of a depth at a time:
       // lanes = (edge slot) x (bin).  An edge's child vector is final once the messages of the child's own
       // children (one depth down, already computed) are multiplied in, in edge order (pictorial.py:44-56).
-      const int i = lane & 7, sl = lane >> 3;
+      const int i = lane & 7;
+      if (os.rsteps >= 0) {   // the schedule tables hold this tree (oc_refine_schedule)
+        const int nst = os.rsteps;
+        uint2 w = os.rstep[0][lane];
+        for (int st = 0; st < nst; ++st) {
+          const uint2 cur_w = w;
+          if (st + 1 < nst) w = os.rstep[st + 1][lane];
+          const bool on = (cur_w.x >> 24) != 0u;
+          const int e = cur_w.x & 255u, c = (cur_w.x >> 8) & 255u, nch = (cur_w.x >> 16) & 255u;
+          if (on) {
+            double acc = eR[c * 8 + i];
+            uint32_t ch = cur_w.y;
+            for (int k = 0; k < nch; ++k, ch >>= 8) acc = acc * msgR[(ch & 255u) * 8 + i];
+            eR[c * 8 + i] = acc;
+          }
+          __syncwarp();
+          if (on) {   // message to parent bin i: the first maximum over the allowed child bins
+            const unsigned pm = os.pmask[e * 8 + i];
+            double best = 0.0;
+            int bidx = -1;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const double val = ((pm >> jj) & 1u) ? eR[c * 8 + jj] : 0.0;
+              if (bidx < 0 || val > best) { best = val; bidx = jj; }
+            }
+            msgR[e * 8 + i] = best;
+            bpR[e * 8 + i] = (uint8_t)bidx;
+          }
+          __syncwarp();
+        }
+        double acc = 0.0;
+        if (lane < 8) {
+          acc = eR[p.root_idx * 8 + lane];
+          uint32_t ch = os.rroot;
+          for (int k = 0; k < os.rroot_n; ++k, ch >>= 8) acc = acc * msgR[(ch & 255u) * 8 + lane];
+        }
+        double best = acc;   // lane 0: root argmax, first maximum, from the other lanes' registers
+        int bidx = 0;
+#pragma unroll
+        for (int b = 1; b < 8; ++b) {
+          const double v = __shfl_sync(0xffffffffu, acc, b);
+          if (v > best) { best = v; bidx = b; }
+        }
+        if (lane == 0) s.bin[p.root_idx] = bidx;
+        __syncwarp();
+        for (int d = 0; d < os.max_depth; ++d) {   // back-tracking: parents before children, a lane per edge
+          const uint32_t wb = os.rback[d][lane];
+          if (wb >> 24) s.bin[(wb >> 16) & 255u] = bpR[(wb & 255u) * 8 + s.bin[(wb >> 8) & 255u]];
+          __syncwarp();
+        }
+      } else {
+      const int sl = lane >> 3;
       for (int d = os.max_depth; d >= 1; --d)
         for (int c0 = os.bt_start[d]; c0 < os.bt_start[d + 1]; c0 += 4) {
           const bool on = c0 + sl < os.bt_start[d + 1];
@@ -838,6 +939,7 @@ __device__ __forceinline__ void refine_levels8(const RpsmParams& p, OcShared& os
           s.bin[s.edge_c[e]] = bpR[e * 8 + s.bin[s.edge_p[e]]];
         }
         __syncwarp();
+      }
       }
       if (lane < J) {
         const int b = s.bin[lane];
@@ -1182,17 +1284,23 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
     oc_mbar_init(mbar);
   }
   __syncthreads();
-  for (int t = tid; t < E * nb0; t += T) {
-    const int e = t / nb0, d = t - e * nb0;
-    const uint32_t* row0 = p.pair_bits + (size_t)e * nb0 * words0;
-    if ((__ldg(row0 + (d >> 5)) >> (d & 31)) & 1u) {
-      int dy, dx, dz;
-      bin_coords(n0, d, dy, dx, dz);
-      atomicMax(&os.reach[e], max(dy, max(dx, dz)));
+  if (warp == 0) {   // thread 0 builds the tree program while the other warps scan row 0 of every edge for its reach
+    if (tid == 0) oc_build_program(os, J, E, p.root_idx, L.nsm + L.nspill);
+    __syncwarp();
+    oc_refine_schedule(os, J, E, p.root_idx);
+  } else {
+    for (int t = tid - 32; t < E * nb0; t += T - 32) {
+      const int e = t / nb0, d = t - e * nb0;
+      const uint32_t* row0 = p.pair_bits + (size_t)e * nb0 * words0;
+      if ((__ldg(row0 + (d >> 5)) >> (d & 31)) & 1u) {
+        int dy, dx, dz;
+        bin_coords(n0, d, dy, dx, dz);
+        atomicMax(&os.reach[e], max(dy, max(dx, dz)));
+      }
     }
   }
   __syncthreads();
-  if (tid == 0) oc_build_program(os, J, E, p.root_idx, L.nsm + L.nspill);
+  if (tid == 0) oc_table_offsets(os, E);
   __syncthreads();
   if (os.prog_err || os.doff[E] > L.dzm_cap) {
     // edges that do not form a tree over all joints, or a max_reach smaller than the table's real reach: the
