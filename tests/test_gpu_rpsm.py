@@ -288,6 +288,46 @@ def test_rpsm_onchip_spills_vectors_for_deep_trees(pict):
     assert np.array_equal(t_on[0], rtrace) and np.array_equal(p_on[0], ref)
 
 
+def test_rpsm_onchip_bushy_tree(pict):
+    """A root with six children, each with a child and a grandchild chain of its own kind: more than four edges per
+    tree depth (several four-edge steps per depth, in the level-0 back-tracking and in the refinement) and a root
+    with more children than the refinement's schedule tables hold, so the 8-bin max-product takes its table-free
+    form.  On-chip = generic kernel = oracle, bins at every level and poses."""
+    from pose_unsupervised_b200.multiviews.body import HumanBody
+    J = 17
+    children = [[] for _ in range(J)]
+    children[0] = [1, 2, 3, 4, 5, 6]
+    for k in range(1, 7):
+        children[k] = [k + 6]                          # 7..12
+    children[7] = [13, 14]
+    children[9] = [15]
+    children[15] = [16]
+    names = ['j%d' % i for i in range(J)]
+    body = HumanBody(names, children, 0)
+    obody = OracleBody(names, children, 0)
+    edges = obody.edges()
+    cfg = rpsm_config(depth=3)
+    pose = synth.random_poses(1, seed=15)[0]
+    cams = synth.camera_ring(4, seed=16)
+    boxes = synth.crop_box(cams, pose)
+    hm = synth.gaussian_heatmaps(cams, boxes, pose, 64, 256, 2.0, 0.02, seed=17)
+    limb = synth.limb_lengths(pose, edges)
+    avg = {e: min(max(limb[e], 150.0), 300.0) for e in edges}   # short limbs: the offset lists stay on chip
+    table = pict.PairwiseTable.from_limb_lengths(avg, body, 2000, 16)
+    assert table.offset_only and table.max_reach <= 5
+    nframes = 3
+    args = (cams * nframes, np.repeat(hm[None], nframes, 0), np.array([b['center'] for b in boxes] * nframes),
+            np.array([b['scale'] for b in boxes] * nframes), np.repeat(pose[0][None], nframes, 0),
+            np.repeat(np.array([[limb[e] for e in edges]]), nframes, 0), table, cfg, body)
+    p_on, t_on = pict.rpsm_batch(*args, return_trace=True, onchip=True)
+    p_gen, t_gen = pict.rpsm_batch(*args, return_trace=True, onchip=False)
+    assert np.array_equal(t_on, t_gen) and np.array_equal(p_on, p_gen)
+    ref, rtrace = opict.rpsm(cams, hm, boxes, pose[0], limb, opict.level0_pairwise(2000, avg, 16, obody), cfg,
+                             obody, return_trace=True)
+    for f in range(nframes):
+        assert np.array_equal(t_on[f], rtrace) and np.array_equal(p_on[f], ref)
+
+
 def test_rpsm_full_batch_is_repeatable(pict):
     """592 frames (4 per SM) three times: the on-chip kernel's stage hand-off, dynamic task hand-out and
     cross-frame prefetch must give identical bins and poses on every launch."""
