@@ -1034,24 +1034,6 @@ __device__ __forceinline__ double oc_factor(const uint32_t* __restrict__ row0, i
   return val;
 }
 
-// The same candidate offered to the two parents of a lane (it is z-neighbour k' of one and k'-1 of the other).
-__device__ __forceinline__ void oc_cand2(uint32_t o2, uint32_t d8, uint32_t p2, uint32_t base, double& bestA,
-                                         double& bestB, double& v) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred pa, pb, q, f;\n\t"
-      ".reg .b32 s, d;\n\t"
-      "add.u32 s, %3, %5;\n\t"
-      "setp.ne.u32 f, 0, 0;\n\t"
-      "lop3.or.b32 s|q, s, 0x3030, 0x1010, 0x6A, f;\n\t"
-      "add.u32 d, %6, %4;\n\t"
-      "@!q ld.shared.f64 %2, [d];\n\t"
-      "setp.gt.and.f64 pa, %2, %0, !q;\n\t"
-      "setp.gt.and.f64 pb, %2, %1, !q;\n\t"
-      "@pa mov.f64 %0, %2;\n\t"
-      "@pb mov.f64 %1, %2;\n\t"
-      "}" : "+d"(bestA), "+d"(bestB), "+d"(v) : "r"(o2), "r"(d8), "r"(p2), "r"(base) : "memory");
-}
 __device__ __forceinline__ void oc_cand_check(uint32_t o2, uint32_t d8, uint32_t p2, uint32_t base, uint32_t sS) {
 #if PB200_DEBUG_CHECKS   // an in-grid candidate must lie inside the source vector
   const bool inside = (((o2 + p2) & 0x3030u) ^ 0x1010u) == 0u;
@@ -1065,9 +1047,9 @@ __device__ __forceinline__ void oc_cand_check(uint32_t o2, uint32_t d8, uint32_t
 // for the 64 parents (iy, z in [4q, 4q+4), all ix) of task u = 4 iy + q.  A lane owns TWO parents, A = (iy, z0, ix)
 // and B = (iy, z0+1, ix) with z0 = 4q + 2 (lane / 16): a child at z-offset k' from z0 is neighbour k' of A and
 // k'-1 of B, and the allowed z-offsets of a row (oy, ox) come in runs, so most children serve both -- one
-// shared-memory read, two comparisons.  The allowed children of the edge are LISTS of offsets (o2, d8 as in
-// oc_cand, k' in place of k), cut into slices by |oy| and, within a slice, into the children of A only, of
-// both, and of B only; they are the same for every lane, so all lanes walk them in lock step and a lane only
+// shared-memory read and ONE comparison, into a running maximum that both parents take at the end.  The allowed
+// children of the edge are LISTS of offsets (o2, d8 as in oc_cand, k' in place of k), cut into slices by |oy|
+// and, within a slice, into the children of A only, of both, and of B only; they are the same for every lane, so all lanes walk them in lock step and a lane only
 // masks the children that fall outside the grid.  The order of the walk is free: only the VALUE of the maximum
 // is needed here (oc_cand).  sList: shared address of the block's lists, loff / lcnt: the edge's sub-lists.
 __device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, uint32_t sList,
@@ -1079,7 +1061,7 @@ __device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, u
   const int iA = iy * 256 + z0 * 16 + ix;             // memory index (iy, iz, ix) of parent A; B = iA + 16
   const double accA = oc_lds64(sD + (uint32_t)iA * 8u), accB = oc_lds64(sD + (uint32_t)(iA + 16) * 8u);
   const bool skipA = accA == 0.0, skipB = accB == 0.0;   // 0 * (finite max) = 0
-  double bestA = -INFINITY, bestB = -INFINITY;
+  double bestA = -INFINITY, bestB = -INFINITY, bestM = -INFINITY;
   double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
   if (__any_sync(0xffffffffu, !(skipA && skipB))) {
     const uint32_t p2 = (skipA && skipB) ? 0u : (uint32_t)((ix + 8) | ((z0 + 8) << 8));
@@ -1113,7 +1095,7 @@ __device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, u
         }                                                                                         \
       }
 #define OC_CAND_A(o2, d8, v) oc_cand(o2, d8, p2, base, bestA, v)
-#define OC_CAND_AB(o2, d8, v) oc_cand2(o2, d8, p2, base, bestA, bestB, v)
+#define OC_CAND_AB(o2, d8, v) oc_cand(o2, d8, p2, base, bestM, v)
 #define OC_CAND_B(o2, d8, v) oc_cand(o2, d8, p2, base, bestB, v)
       OC_WALK(0, OC_CAND_A)
       OC_WALK(1, OC_CAND_AB)
@@ -1123,6 +1105,9 @@ __device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, u
 #undef OC_CAND_B
 #undef OC_WALK
     }
+    // the shared children went into one running maximum (one comparison each); both parents take it at the end
+    bestA = bestM > bestA ? bestM : bestA;
+    bestB = bestM > bestB ? bestM : bestB;
   }
   // (a finite frame: -inf can only be the initial value, i.e. no allowed child inside the grid)
   bool bad = false;
