@@ -580,7 +580,7 @@ struct OcShared {
   int doff[kRpsmMaxJ + 1];      // offset of edge e in the |dz| table
   uint16_t loff[kRpsmMaxJ][8][3];   // offset / (even) length of the three offset sub-lists of (edge, |oy|):
   uint16_t lcnt[kRpsmMaxJ][8][3];   // children of parent A only, of both parents of a lane, of parent B only
-  int use_flat;                 // 1: the offset lists of all edges fit in shared memory and n0 = 16
+  uint32_t use_flat;            // bit e: edge e's offset lists are in shared memory (n0 = 16 and they fit)
   int child_start[kRpsmMaxJ + 1];
   uint8_t child_edge[kRpsmMaxJ];
   uint8_t samp_joint[kRpsmMaxJ];
@@ -1366,17 +1366,25 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
         }
       }
     __syncthreads();
-    if (tid == 0 && !can) os.use_flat = 0;
-    else if (tid == 0) {   // the sub-lists one after the other
-      int off = 0;
-      for (int e = 0; e < E; ++e)
+    if (tid == 0 && !can) os.use_flat = 0u;
+    else if (tid == 0) {   // the sub-lists one after the other; an edge whose lists no longer fit goes without
+      int off = 0;         // (it takes the per-lane enumeration: same results, slower)
+      uint32_t have = 0u;
+      const int cap = min(L.list_cap, 65535);
+      for (int e = 0; e < E; ++e) {
+        int need = 0;
+        for (int a = 0; a <= os.reach[e]; ++a)
+          for (int sub = 0; sub < 3; ++sub) need += os.lcnt[e][a][sub];
+        if (off + need > cap) continue;
+        have |= 1u << e;
         for (int a = 0; a <= os.reach[e]; ++a)
           for (int sub = 0; sub < 3; ++sub) {
-            os.loff[e][a][sub] = (uint16_t)min(off, 65535);
+            os.loff[e][a][sub] = (uint16_t)off;
             off += os.lcnt[e][a][sub];
           }
-      os.use_flat = (off <= L.list_cap && off < 65535) ? 1 : 0;
-      PB_DCHECK(off <= L.list_cap || os.use_flat == 0, kDbgRpsmList);
+      }
+      os.use_flat = have;
+      PB_DCHECK(off <= L.list_cap, kDbgRpsmList);
     }
     __syncthreads();
     if (os.use_flat) {
@@ -1385,6 +1393,7 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
         const int sub = t / rows, row = t - sub * rows;
         int e, a, x, w;
         row_slot(row, e, a, x, w);
+        if (!((os.use_flat >> e) & 1u)) continue;
         const int ox = x - os.reach[e];
         const uint32_t bits = sub_bits(dzm[row], sub);
         const int o0 = os.loff[e][a][sub];
@@ -1538,7 +1547,7 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
           }
         }
         const bool finite = os.nonfinite == 0;
-        const bool flat = finite && os.use_flat != 0 && op.src < L.nsm && op.dst < L.nsm;
+        const bool flat = finite && ((os.use_flat >> e) & 1u) != 0u && op.src < L.nsm && op.dst < L.nsm;
         const uint32_t* row0 = p.pair_bits + (size_t)e * nb0 * words0;
         bool bad = false;
         for (;;) {

@@ -328,6 +328,32 @@ def test_rpsm_onchip_bushy_tree(pict):
         assert np.array_equal(t_on[f], rtrace) and np.array_equal(p_on[f], ref)
 
 
+def test_rpsm_onchip_long_limbs_overflow_the_lists(pict):
+    """Limbs 20 % longer than H36M's: the child-offset lists of all 16 edges no longer fit next to the energy
+    vectors (3 012 entries for 2 588 places), so the last edges go without and take the per-lane enumeration while
+    the others keep the list walk -- in the same frame.  On-chip = generic kernel = oracle."""
+    from pose_unsupervised_b200.multiviews.body import HumanBody
+    body, obody = HumanBody.h36m17(), h36m17()
+    edges = obody.edges()
+    cfg = rpsm_config(depth=2)
+    avg = {e: 1.2 * float(np.mean([np.linalg.norm(p[e[0]] - p[e[1]]) for p in synth.random_poses(64, seed=99)]))
+           for e in edges}
+    table = pict.PairwiseTable.from_limb_lengths(avg, body, 2000, 16)
+    assert table.offset_only and table.max_reach == 5
+    pose, cams, boxes, hm, limb = _frame(edges, 17, 900)
+    nframes = 3
+    args = (cams * nframes, np.repeat(hm[None], nframes, 0), np.array([b['center'] for b in boxes] * nframes),
+            np.array([b['scale'] for b in boxes] * nframes), np.repeat(pose[0][None], nframes, 0),
+            np.repeat(np.array([[limb[e] for e in edges]]), nframes, 0), table, cfg, body)
+    p_on, t_on = pict.rpsm_batch(*args, return_trace=True, onchip=True)
+    p_gen, t_gen = pict.rpsm_batch(*args, return_trace=True, onchip=False)
+    assert np.array_equal(t_on, t_gen) and np.array_equal(p_on, p_gen)
+    ref, rtrace = opict.rpsm(cams, hm, boxes, pose[0], limb, opict.level0_pairwise(2000, avg, 16, obody), cfg,
+                             obody, return_trace=True)
+    for f in range(nframes):
+        assert np.array_equal(t_on[f], rtrace) and np.array_equal(p_on[f], ref)
+
+
 def test_rpsm_full_batch_is_repeatable(pict):
     """592 frames (4 per SM) three times: the on-chip kernel's stage hand-off, dynamic task hand-out and
     cross-frame prefetch must give identical bins and poses on every launch."""
