@@ -578,8 +578,8 @@ struct OcShared {
   int nops, nsamp, root_buf, prog_err;
   int reach[kRpsmMaxJ];
   int doff[kRpsmMaxJ + 1];      // offset of edge e in the |dz| table
-  uint16_t loff[kRpsmMaxJ][8][3];   // offset / (even) length of the three offset sub-lists of (edge, |oy|):
-  uint16_t lcnt[kRpsmMaxJ][8][3];   // children of parent A only, of both parents of a lane, of parent B only
+  uint16_t loff[kRpsmMaxJ][8][2];   // offset / (even) length of the two offset sub-lists of (edge, |oy|): children
+  uint16_t lcnt[kRpsmMaxJ][8][2];   // of ONE of a lane's two parents (A, B alternating), children of both
   uint32_t use_flat;            // bit e: edge e's offset lists are in shared memory (n0 = 16 and they fit)
   int child_start[kRpsmMaxJ + 1];
   uint8_t child_edge[kRpsmMaxJ];
@@ -1053,8 +1053,8 @@ __device__ __forceinline__ void oc_cand_check(uint32_t o2, uint32_t d8, uint32_t
 // masks the children that fall outside the grid.  The order of the walk is free: only the VALUE of the maximum
 // is needed here (oc_cand).  sList: shared address of the block's lists, loff / lcnt: the edge's sub-lists.
 __device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, uint32_t sList,
-                                                     const uint16_t (*__restrict__ loff)[3],
-                                                     const uint16_t (*__restrict__ lcnt)[3],
+                                                     const uint16_t (*__restrict__ loff)[2],
+                                                     const uint16_t (*__restrict__ lcnt)[2],
                                                      const uint32_t* __restrict__ row0, int r, int u) {
   const int lane = threadIdx.x & 31;
   const int ix = lane & 15, z0 = 4 * (u & 3) + 2 * (lane >> 4), iy = u >> 2;
@@ -1070,7 +1070,7 @@ __device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, u
       const int aoy = oy < 0 ? -oy : oy;
       const uint32_t base = sS + (uint32_t)((iA + oy * 256) * 8);
       // each sub-list four entries per trip (its length is even), the loaded energies in v0..v3
-#define OC_WALK(SUB, CAND)                                                                      \
+#define OC_WALK(SUB, EVEN, ODD)                                                                 \
       {                                                                                           \
         uint32_t la = sList + (uint32_t)loff[aoy][SUB] * 8u;                                      \
         const int n = lcnt[aoy][SUB];                                                             \
@@ -1081,28 +1081,21 @@ __device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, u
           oc_cand_check(e.z, e.w, p2, base, sS);                                                  \
           oc_cand_check(g.x, g.y, p2, base, sS);                                                  \
           oc_cand_check(g.z, g.w, p2, base, sS);                                                  \
-          CAND(e.x, e.y, v0);                                                                     \
-          CAND(e.z, e.w, v1);                                                                     \
-          CAND(g.x, g.y, v2);                                                                     \
-          CAND(g.z, g.w, v3);                                                                     \
+          oc_cand(e.x, e.y, p2, base, EVEN, v0);                                                  \
+          oc_cand(e.z, e.w, p2, base, ODD, v1);                                                   \
+          oc_cand(g.x, g.y, p2, base, EVEN, v2);                                                  \
+          oc_cand(g.z, g.w, p2, base, ODD, v3);                                                   \
         }                                                                                         \
         if (t < n) {                                                                              \
           const uint4 e = oc_lds128(la);                                                          \
           oc_cand_check(e.x, e.y, p2, base, sS);                                                  \
           oc_cand_check(e.z, e.w, p2, base, sS);                                                  \
-          CAND(e.x, e.y, v0);                                                                     \
-          CAND(e.z, e.w, v1);                                                                     \
+          oc_cand(e.x, e.y, p2, base, EVEN, v0);                                                  \
+          oc_cand(e.z, e.w, p2, base, ODD, v1);                                                   \
         }                                                                                         \
       }
-#define OC_CAND_A(o2, d8, v) oc_cand(o2, d8, p2, base, bestA, v)
-#define OC_CAND_AB(o2, d8, v) oc_cand(o2, d8, p2, base, bestM, v)
-#define OC_CAND_B(o2, d8, v) oc_cand(o2, d8, p2, base, bestB, v)
-      OC_WALK(0, OC_CAND_A)
-      OC_WALK(1, OC_CAND_AB)
-      OC_WALK(2, OC_CAND_B)
-#undef OC_CAND_A
-#undef OC_CAND_AB
-#undef OC_CAND_B
+      OC_WALK(0, bestA, bestB)   // a run's first child is A's alone, the one past its end B's alone: they alternate
+      OC_WALK(1, bestM, bestM)   // the children in between are shared
 #undef OC_WALK
     }
     // the shared children went into one running maximum (one comparison each); both parents take it at the end
@@ -1325,22 +1318,26 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
   }
   __syncthreads();
   // ---- the edges' child-offset lists (fast form of the max-product, n0 = 16) ------------------------
-  // Row (e, |oy|, ox) has the allowed z-offsets K (from its |dz| set).  For the parent pair (z0, z0+1) of a lane
-  // the children at z0 + k' are: of A only, k' in K \ (K+1); of both, K & (K+1); of B only, (K+1) \ K.  Each
-  // slice (e, |oy|) stores the three sub-lists, rows in order, each padded to an even number of entries with
-  // one that is outside for every parent.  Bit (k' + 15) of a 32-bit word stands for k' = -15..16.
+  // Row (e, |oy|, ox) has the allowed z-offsets K (from its |dz| set), a union of runs.  For the parent pair
+  // (z0, z0+1) of a lane the children at z0 + k' are: of A only, k' in K \ (K+1) -- the first of each run; of B
+  // only, (K+1) \ K -- one past the end of each run; of both, K & (K+1).  Each slice (e, |oy|) stores two
+  // sub-lists, rows in order: the runs' (A-only, B-only) pairs, and the shared children, padded to an even number
+  // of entries with one that is outside for every parent.  Bit (k' + 15) of a 32-bit word stands for k' = -15..16.
   {
     int32_t* rowoff = reinterpret_cast<int32_t*>(vec_sm);   // scratch: the energy vectors are not in use yet
     const int rows = os.doff[E];
-    auto sub_bits = [](unsigned m, int sub) -> uint32_t {
+    auto sub_bits = [](unsigned m, int which) -> uint32_t {   // 0: A only, 1: both, 2: B only
       uint32_t K = 0u;
       for (int d = 0; d < 16; ++d)
         if ((m >> d) & 1u) K |= (1u << (15 + d)) | (1u << (15 - d));
       const uint32_t K1 = K << 1;
-      return sub == 0 ? (K & ~K1) : sub == 1 ? (K & K1) : (K1 & ~K);
+      return which == 0 ? (K & ~K1) : which == 1 ? (K & K1) : (K1 & ~K);
     };
-    const bool can = n0 == 16 && 6 * rows * 4 <= L.nsm * L.vec_stride * 8;   // block-uniform
-    int32_t* pre = rowoff + 3 * rows;
+    auto entry = [](int ox, int k) {
+      return make_uint2((uint32_t)((ox + 8) + (k + 8) * 256), (uint32_t)((k * 16 + ox) * 8));
+    };
+    const bool can = n0 == 16 && 4 * rows * 4 <= L.nsm * L.vec_stride * 8;   // block-uniform
+    int32_t* pre = rowoff + 2 * rows;
     auto row_slot = [&](int row, int& e, int& a, int& x, int& w) {   // row -> (edge, |oy|, column, columns)
       e = 0;
       while (row >= os.doff[e + 1]) ++e;
@@ -1350,10 +1347,13 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
       x = local - a * w;
     };
     if (can)
-      for (int t = tid; t < 3 * rows; t += T) rowoff[t] = __popc(sub_bits(dzm[t % rows], t / rows));   // entries per row
+      for (int t = tid; t < 2 * rows; t += T) {   // entries per row: two per run, or the shared ones
+        const unsigned m = dzm[t % rows];
+        rowoff[t] = t < rows ? 2 * __popc(sub_bits(m, 0)) : __popc(sub_bits(m, 1));
+      }
     __syncthreads();
     if (can)
-      for (int t = tid; t < 3 * rows; t += T) {   // a row's offset within its sub-list; the last row knows the length
+      for (int t = tid; t < 2 * rows; t += T) {   // a row's offset within its sub-list; the last row knows the length
         const int sub = t / rows, row = t - sub * rows;
         int e, a, x, w;
         row_slot(row, e, a, x, w);
@@ -1374,11 +1374,11 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
       for (int e = 0; e < E; ++e) {
         int need = 0;
         for (int a = 0; a <= os.reach[e]; ++a)
-          for (int sub = 0; sub < 3; ++sub) need += os.lcnt[e][a][sub];
+          for (int sub = 0; sub < 2; ++sub) need += os.lcnt[e][a][sub];
         if (off + need > cap) continue;
         have |= 1u << e;
         for (int a = 0; a <= os.reach[e]; ++a)
-          for (int sub = 0; sub < 3; ++sub) {
+          for (int sub = 0; sub < 2; ++sub) {
             os.loff[e][a][sub] = (uint16_t)off;
             off += os.lcnt[e][a][sub];
           }
@@ -1389,21 +1389,28 @@ __global__ void __launch_bounds__(kOcThreads, 1) rpsm_onchip_kernel(const RpsmPa
     __syncthreads();
     if (os.use_flat) {
       uint2* list = reinterpret_cast<uint2*>(smem_raw + L.list_off);
-      for (int t = tid; t < 3 * rows; t += T) {
+      for (int t = tid; t < 2 * rows; t += T) {
         const int sub = t / rows, row = t - sub * rows;
         int e, a, x, w;
         row_slot(row, e, a, x, w);
         if (!((os.use_flat >> e) & 1u)) continue;
         const int ox = x - os.reach[e];
-        const uint32_t bits = sub_bits(dzm[row], sub);
         const int o0 = os.loff[e][a][sub];
         int o = o0 + pre[t];
-        for (int b = 0; b < 32; ++b)
-          if ((bits >> b) & 1u) {
-            const int k = b - 15;
-            list[o++] = make_uint2((uint32_t)((ox + 8) + (k + 8) * 256), (uint32_t)((k * 16 + ox) * 8));
+        if (sub == 0) {
+          uint32_t A = sub_bits(dzm[row], 0), B = sub_bits(dzm[row], 2);   // as many bits in one as in the other
+          while (A != 0u && B != 0u) {
+            list[o++] = entry(ox, __ffs(A) - 16);
+            list[o++] = entry(ox, __ffs(B) - 16);
+            A &= A - 1u;
+            B &= B - 1u;
           }
-        if (x == w - 1 && ((o - o0) & 1)) list[o] = make_uint2(0x3030u, 0u);   // padding
+        } else {
+          const uint32_t bits = sub_bits(dzm[row], 1);
+          for (int b = 0; b < 32; ++b)
+            if ((bits >> b) & 1u) list[o++] = entry(ox, b - 15);
+          if (x == w - 1 && ((o - o0) & 1)) list[o] = make_uint2(0x3030u, 0u);   // padding
+        }
       }
     }
     // the fast form's 64 warp tasks, longest first: a task walks the slices |oy| its plane iy has inside the grid
