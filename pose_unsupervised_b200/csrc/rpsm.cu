@@ -1049,7 +1049,8 @@ __device__ __forceinline__ void oc_cand_check(uint32_t o2, uint32_t d8, uint32_t
 // k'-1 of B, and the allowed z-offsets of a row (oy, ox) come in runs, so most children serve both -- one
 // shared-memory read and ONE comparison, into a running maximum that both parents take at the end.  The allowed
 // children of the edge are LISTS of offsets (o2, d8 as in oc_cand, k' in place of k), cut into slices by |oy|
-// and, within a slice, into the children of A only, of both, and of B only; they are the same for every lane, so all lanes walk them in lock step and a lane only
+// and, within a slice, into the runs' ends (A's own child and B's own child of each run, alternating) and the
+// children of both; they are the same for every lane, so all lanes walk them in lock step and a lane only
 // masks the children that fall outside the grid.  The order of the walk is free: only the VALUE of the maximum
 // is needed here (oc_cand).  sList: shared address of the block's lists, loff / lcnt: the edge's sub-lists.
 __device__ __forceinline__ bool oc_maxprod_unit_flat(uint32_t sS, uint32_t sD, uint32_t sList,

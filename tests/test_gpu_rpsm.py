@@ -330,7 +330,7 @@ def test_rpsm_onchip_bushy_tree(pict):
 
 def test_rpsm_onchip_long_limbs_overflow_the_lists(pict):
     """Limbs 20 % longer than H36M's: the child-offset lists of all 16 edges no longer fit next to the energy
-    vectors (3 012 entries for 2 588 places), so the last edges go without and take the per-lane enumeration while
+    vectors (2 944 entries for 2 716 places), so the last edges go without and take the per-lane enumeration while
     the others keep the list walk -- in the same frame.  On-chip = generic kernel = oracle."""
     from pose_unsupervised_b200.multiviews.body import HumanBody
     body, obody = HumanBody.h36m17(), h36m17()
